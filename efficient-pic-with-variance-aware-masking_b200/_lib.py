@@ -1,0 +1,133 @@
+"""ctypes binding of libpic_latent.so (the C ABI declared in include/pic_latent.h).
+
+The library is built in-tree (``build()`` below or ``__graft_entry__.build()``) with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no CPU fallback: if the shared
+object is missing, or a tensor is not a CUDA tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libpic_latent.so")
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu")]
+_HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_select.cuh")] + [
+    os.path.join(_ROOT, "include", "pic_latent.h")]
+
+PIC_OK = 0
+PIC_ERR_INVALID_ARGUMENT = -1
+PIC_ERR_TOO_LARGE = -2
+PIC_ERR_WORKSPACE = -3
+PIC_ERR_CUDA = -4
+PIC_ERR_UNALIGNED = -5
+
+Q_ONES = -1.0
+Q_ZEROS = 2.0
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/pic_latent.h
+SIGNATURES = {
+    "pic_version": (C.c_int, []),
+    "pic_error_string": (C.c_char_p, [C.c_int]),
+    "pic_last_cuda_error": (C.c_int, []),
+    "pic_fused_max_elems": (_i64, []),
+    "pic_workspace_bytes": (_sz, [_i64, _i64]),
+    "pic_select_threshold": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pic_select_state_bytes": (_sz, [_i64]),
+    "pic_hist_words": (_i64, []),
+    "pic_select_begin": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),
+    "pic_hist_round": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "pic_select_advance": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "pic_select_finish": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "pic_channel_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pic_mask_from_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "pic_slice_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _f32,
+                                    _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pic_slice_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64,
+                                     _vp, _vp, _vp, _vp, _vp]),
+    "pic_gaussian_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
+    "pic_gaussian_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32,
+                                        _vp, _vp, _vp, _vp]),
+    "pic_build_indexes": (C.c_int, [_vp, _i64, _vp, _i32, _f32, _vp, _vp]),
+    "pic_quantize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "pic_dequantize": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "pic_log_sum": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "pic_host_pipeline_bytes": (_sz, [_i64, _i64]),
+    "pic_slice_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _f32, _f32,
+                                         _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+}
+
+_lib = None
+
+
+class PicCudaError(RuntimeError):
+    pass
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libpic_latent.so")
+
+
+def needs_build() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in _SOURCES + _HEADERS if os.path.isfile(p))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles every CUDA source of the package for sm_100a into libpic_latent.so (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    srcs = [s for s in _SOURCES if os.path.isfile(s)]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)  # the image's CC points at a gcc without OpenMP specs
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def lib():
+    """Loads the C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise PicCudaError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the PIC latent path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Maps C-ABI error codes to the exceptions the reference API raises."""
+    if rc == PIC_OK:
+        return
+    msg = lib().pic_error_string(rc).decode()
+    if rc == PIC_ERR_TOO_LARGE:
+        raise RuntimeError("quantile() input tensor is too large")  # torch.quantile's message
+    if rc == PIC_ERR_INVALID_ARGUMENT:
+        raise ValueError(f"{what}: {msg}")
+    if rc == PIC_ERR_CUDA:
+        raise PicCudaError(f"{what}: CUDA error {lib().pic_last_cuda_error()}")
+    raise RuntimeError(f"{what}: {msg} ({rc})")

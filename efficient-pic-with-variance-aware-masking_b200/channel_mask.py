@@ -1,0 +1,108 @@
+"""Drop-in for the reference's ``layers/channel_mask.py`` (ChannelMask, ste_round).
+
+Same class name, constructor, method names, argument meaning, return dtype (f32 masks) and
+error behaviour; the per-image ``torch.quantile`` sort + compare loop is replaced by the exact
+radix-select kernels of libpic_latent.so (one launch for the whole batch, no host sync).
+
+Reference lines: ChannelMask.forward 89-156 (live branch 132-151, "two-levels" 152-153),
+ProgMask 18-49, apply_noise 81-86, ste_round 5-6.  ``delta_mask`` (52-78) and the ``cust_map``
+quantile branch (96-121) are dead/broken in the reference (chained tensor comparison raises;
+undefined ``bs, ch, w, h``) and are not reproduced beyond their pr>=10 / pr==0 shortcuts.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class _SteRound(torch.autograd.Function):
+    """torch.round(x) - x.detach() + x: value of round(), identity gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.quantize(x, "ste")
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def ste_round(x: torch.Tensor) -> torch.Tensor:
+    return _SteRound.apply(x)
+
+
+class ChannelMask(nn.Module):
+    def __init__(self, mask_policy):
+        super().__init__()
+        self.mask_policy = mask_policy
+
+    # ------------------------------------------------------------------ ProgMask (18-49)
+    def ProgMask(self, scale, pr):
+        """`scale` is a list of per-slice blocks [1, ch, w, h]; returns the stacked masks
+        [len(scale)*bs, ch, w, h] (f32).  All blocks go through ONE launch."""
+        if len(scale) == 0:
+            raise RuntimeError("stack expects a non-empty TensorList")
+        blocks = [b if b.is_contiguous() else b.contiguous() for b in scale]
+        shape0 = blocks[0].shape
+        same = all(b.shape == shape0 for b in blocks)
+        if not same:
+            # ragged blocks cannot be stacked by the reference either (torch.stack raises)
+            raise RuntimeError("stack expects each tensor to be equal size")
+        bs, ch, w, h = shape0
+        stacked = torch.cat([b.reshape(bs, ch * w * h) for b in blocks], dim=0)
+        q01 = ops.pr_to_q01(pr)
+        mask = ops.channel_mask(stacked, stacked.shape[0], q01)
+        return mask.reshape(len(blocks) * bs, ch, w, h)
+
+    def delta_mask(self, scale, pr_bar, pr):
+        raise NotImplementedError("delta_mask is dead code in the reference (chained tensor comparison raises)")
+
+    # ------------------------------------------------------------------ apply_noise (81-86)
+    def apply_noise(self, mask, training):
+        if training:
+            mask = ste_round(mask)
+        else:
+            mask = ops.quantize(mask, "dequantize")  # torch.round
+        return mask
+
+    # ------------------------------------------------------------------ forward (89-156)
+    def forward(self, scale, pr=0, mask_pol="point-based-std", ravel=False, cust_map=None):
+        if cust_map is not None:
+            if pr >= 10:
+                return torch.ones_like(cust_map).to(scale.device)
+            elif pr == 0:
+                return torch.zeros_like(cust_map).to(scale.device)
+            raise NotImplementedError("cust_map quantile branch is broken in the reference (undefined bs/ch/w/h)")
+
+        if mask_pol is None:
+            mask_pol = self.mask_policy
+
+        shapes = scale.shape
+        if ravel is False:
+            bs, ch, w, h = shapes
+        else:
+            bs, d = shapes
+
+        if mask_pol == "point-based-std":
+            if pr >= 10:
+                return torch.ones_like(scale)
+            elif pr == 0:
+                return torch.zeros_like(scale)
+            assert scale is not None
+            q01 = ops.pr_to_q01(pr)
+            mask = ops.channel_mask(scale, bs, q01)
+            return mask.reshape(shapes)
+        elif mask_pol == "two-levels":
+            return torch.zeros_like(scale) if pr == 0 else torch.ones_like(scale)
+        else:
+            raise NotImplementedError()
+
+    # ------------------------------------------------------------------ extensions (not in the reference)
+    def forward_multi(self, scale, prs):
+        """One quality level per image/unit: `prs` is a sequence of len(scale) qualities or a
+        prepared per-unit q01 tensor (ops.q01_tensor)."""
+        bs = scale.shape[0]
+        q = prs if isinstance(prs, torch.Tensor) else ops.q01_tensor(prs, scale.device)
+        return ops.channel_mask(scale, bs, q).reshape(scale.shape)

@@ -1,0 +1,1108 @@
+// pic_latent.cu -- kernels + C ABI of libpic_latent.so (sm_100a only).
+//
+// Hot path per progressive slice (reference: models/pic.py:583-584, 621-629, 809-820):
+//   select threshold (torch.quantile semantics) -> mask -> mean substitution -> round/noise
+//   quantisation -> Gaussian likelihood -> scale-table index / symbols / rate.
+//
+// Kernels
+//   slice_fused_kernel      one CTA per unit (n <= kFusedMaxElems): std tile -> order-preserving
+//                           keys in shared memory + round-0 histogram in the same sweep,
+//                           3-round radix select in shared memory, then the apply sweep reads
+//                           std back from shared memory.  HBM traffic = compulsory bytes only.
+//   hist_round_kernel /     multi-CTA select for large units and for spatially tiled units
+//   select_advance_kernel / (histograms merged in global memory; all-reducible between rounds)
+//   select_finish_kernel
+//   slice_apply_kernel      elementwise apply with given thresholds (tile per CTA)
+//   slice_backward_kernel   fused backward
+//   gaussian_* / build_indexes / quantize / dequantize / log_sum   un-fused operators
+// All global accesses are 128-bit when n % 4 == 0 and the pointers are 16-byte aligned.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pic_latent.h"
+#include "pic_math.cuh"
+#include "pic_select.cuh"
+
+namespace pic {
+
+// ------------------------------------------------------------------------------------------
+// host-side helpers
+// ------------------------------------------------------------------------------------------
+static thread_local int g_last_cuda_error = 0;
+
+#define PIC_CUDA_CHECK(expr)                                   \
+    do {                                                       \
+        cudaError_t e__ = (expr);                              \
+        if (e__ != cudaSuccess) {                              \
+            pic::g_last_cuda_error = static_cast<int>(e__);    \
+            return PIC_ERR_CUDA;                               \
+        }                                                      \
+    } while (0)
+
+static int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = static_cast<int>(e);
+        return PIC_ERR_CUDA;
+    }
+    return PIC_OK;
+}
+
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+constexpr int kFusedMaxElems = 55296;   // 216 KiB of keys + 8 KiB histogram + scratch <= 227 KiB
+constexpr int kScratchWords = 64;
+constexpr int kTableSmem = 64;
+constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
+constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
+constexpr int kRoundChunk = 16384;         // elements per CTA in hist_round_kernel
+
+struct SliceParams {
+    const float *y_top, *y_base, *mu, *std, *q01_per_unit, *thr_in, *noise, *table;
+    float q01, scale_bound, lik_bound;
+    int table_len;
+    int64_t n, units;
+    float *mask, *y_hat, *lik;
+    int32_t *idx, *symbols;
+    float *thr_out, *a_out, *b_out;
+    double *rate;
+    int apply_kind;  // 0: select only, 1: mask only, 2: full slice
+};
+
+struct SelectState {
+    uint32_t lo, hi;
+    float w, q;
+    uint32_t prefix, rank, below_total;
+    uint32_t a_key, b_key, need_min, nan_flag, count;
+    int32_t mode;
+    uint32_t pad[3];
+};
+static_assert(sizeof(SelectState) == 64, "SelectState must stay 64 bytes");
+
+// ------------------------------------------------------------------------------------------
+// per-element apply
+// ------------------------------------------------------------------------------------------
+struct ElemOut {
+    float m, y_hat, lik;
+    int32_t idx, sym;
+};
+
+template <bool TRAIN>
+__device__ __forceinline__ ElemOut apply_one(const SliceParams &p, float s, float yt, float yb,
+                                             float mu, float nz, int mode, float thr,
+                                             const float *tbl, bool tbl64) {
+    ElemOut o;
+    const float m = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s >= thr) ? 1.0f : 0.0f);
+    const float r = p.y_base ? __fsub_rn(yt, yb) : yt;       // pic.py:583-584
+    const float d = __fsub_rn(r, mu);                         // pic.py:625
+    const float y_m = __fmul_rn(d, m);                        // pic.py:626
+    const float s_m = __fmul_rn(s, m);                        // pic.py:628 (scale*block_mask)
+    const float out = TRAIN ? __fadd_rn(y_m, nz) : rintf(y_m);  // quantize("noise"|"dequantize")
+    o.m = m;
+    o.lik = (p.lik || p.rate) ? likelihood(out, s_m, p.scale_bound, p.lik_bound) : 0.0f;
+    const float rd = rintf(d);
+    const float ste = __fadd_rn(__fsub_rn(rd, d), d);         // ste_round forward value
+    o.y_hat = __fadd_rn(__fmul_rn(ste, m), mu);               // pic.py:629
+    o.idx = 0;
+    if (p.idx) o.idx = tbl64 ? scale_index64(s_m, p.scale_bound, tbl) : scale_index(s_m, p.scale_bound, tbl, p.table_len);
+    o.sym = __float2int_rn(y_m);                              // quantize(.., "symbols")
+    return o;
+}
+
+// Applies the slice arithmetic to elements [0, len) of a unit-local range starting at global
+// element offset `off`.  keys != nullptr: std comes from the shared-memory key tile (index 0 ==
+// first element of the range); otherwise from global memory.
+template <bool TRAIN, bool VEC, int THREADS>
+__device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, int len,
+                                             const uint32_t *keys, int mode, float thr,
+                                             const float *tbl, bool tbl64) {
+    float rate_acc = 0.0f;
+    const int tid = threadIdx.x;
+    const bool full = p.apply_kind == 2;
+    if (VEC) {
+        const int nvec = len >> 2;
+        const float4 *std4 = reinterpret_cast<const float4 *>(p.std + off);
+        const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top + off);
+        const float4 *yb4 = p.y_base ? reinterpret_cast<const float4 *>(p.y_base + off) : nullptr;
+        const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu + off);
+        const float4 *nz4 = TRAIN ? reinterpret_cast<const float4 *>(p.noise + off) : nullptr;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+        for (int j = tid; j < nvec; j += THREADS) {
+            float s[4];
+            if (keys) {
+                const uint4 k = k4[j];
+                s[0] = key_to_float(k.x); s[1] = key_to_float(k.y);
+                s[2] = key_to_float(k.z); s[3] = key_to_float(k.w);
+            } else {
+                const float4 v = __ldg(std4 + j);
+                s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+            }
+            if (!full) {
+                float mk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    mk[e] = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s[e] >= thr) ? 1.0f : 0.0f);
+                reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(mk[0], mk[1], mk[2], mk[3]);
+                continue;
+            }
+            const float4 ytv = __ldg(yt4 + j);
+            const float4 muv = __ldg(mu4 + j);
+            float4 ybv = make_float4(0.f, 0.f, 0.f, 0.f), nzv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yb4) ybv = __ldg(yb4 + j);
+            if (TRAIN) nzv = __ldg(nz4 + j);
+            const float yt[4] = {ytv.x, ytv.y, ytv.z, ytv.w}, yb[4] = {ybv.x, ybv.y, ybv.z, ybv.w};
+            const float mu[4] = {muv.x, muv.y, muv.z, muv.w}, nz[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
+            ElemOut o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                o[e] = apply_one<TRAIN>(p, s[e], yt[e], yb[e], mu[e], nz[e], mode, thr, tbl, tbl64);
+                if (p.rate) rate_acc += logf(o[e].lik);
+            }
+            if (p.mask) reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(o[0].m, o[1].m, o[2].m, o[3].m);
+            if (p.y_hat) reinterpret_cast<float4 *>(p.y_hat + off)[j] = make_float4(o[0].y_hat, o[1].y_hat, o[2].y_hat, o[3].y_hat);
+            if (p.lik) reinterpret_cast<float4 *>(p.lik + off)[j] = make_float4(o[0].lik, o[1].lik, o[2].lik, o[3].lik);
+            if (p.idx) reinterpret_cast<int4 *>(p.idx + off)[j] = make_int4(o[0].idx, o[1].idx, o[2].idx, o[3].idx);
+            if (p.symbols) reinterpret_cast<int4 *>(p.symbols + off)[j] = make_int4(o[0].sym, o[1].sym, o[2].sym, o[3].sym);
+        }
+    } else {
+        for (int j = tid; j < len; j += THREADS) {
+            const float s = keys ? key_to_float(keys[j]) : __ldg(p.std + off + j);
+            if (!full) {
+                p.mask[off + j] = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s >= thr) ? 1.0f : 0.0f);
+                continue;
+            }
+            const float yt = __ldg(p.y_top + off + j);
+            const float yb = p.y_base ? __ldg(p.y_base + off + j) : 0.0f;
+            const float mu = __ldg(p.mu + off + j);
+            const float nz = TRAIN ? __ldg(p.noise + off + j) : 0.0f;
+            const ElemOut o = apply_one<TRAIN>(p, s, yt, yb, mu, nz, mode, thr, tbl, tbl64);
+            if (p.rate) rate_acc += logf(o.lik);
+            if (p.mask) p.mask[off + j] = o.m;
+            if (p.y_hat) p.y_hat[off + j] = o.y_hat;
+            if (p.lik) p.lik[off + j] = o.lik;
+            if (p.idx) p.idx[off + j] = o.idx;
+            if (p.symbols) p.symbols[off + j] = o.sym;
+        }
+    }
+    return rate_acc;
+}
+
+// block reduction of the per-thread rate partials in f64; result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum_f64(float v, double *sh /* THREADS/32 doubles */) {
+    double d = static_cast<double>(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = d;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < THREADS / 32; ++w) total += sh[w];
+    __syncthreads();
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused kernel: one CTA per unit
+// ------------------------------------------------------------------------------------------
+template <bool TRAIN, bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = static_cast<int>(p.n);
+    const int n_pad = (n + 3) & ~3;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *hist = keys + n_pad;
+    uint32_t *scratch = hist + kHistBins;
+    float *tbl = reinterpret_cast<float *>(scratch + kScratchWords);
+    double *red = reinterpret_cast<double *>(tbl + kTableSmem);
+    const int tid = threadIdx.x;
+    const bool tbl64 = (p.table_len == kTableSmem) && p.idx;
+    if (tbl64 && tid < kTableSmem) tbl[tid] = p.table[tid];
+    const float *tbl_ptr = tbl64 ? tbl : p.table;
+
+    for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int64_t off = u * p.n;
+        const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
+        const int mode = unit_mode(q);
+        float thr = (mode == kModeOnes) ? -INFINITY : INFINITY;
+        float a_val = thr, b_val = thr;
+        bool staged = false;
+        if (p.thr_in && mode == kModeThreshold) {
+            thr = p.thr_in[u];
+            a_val = b_val = thr;
+        } else if (mode == kModeThreshold) {
+            // ---- sweep 1: std -> keys in smem, round-0 histogram, NaN flag --------------
+            for (int j = tid; j < kHistBins; j += THREADS) hist[j] = 0u;
+            if (tid == 0) scratch[39] = 0u;
+            __syncthreads();
+            bool has_nan = false;
+            if (VEC) {
+                const float4 *std4 = reinterpret_cast<const float4 *>(p.std + off);
+                const int nvec = n >> 2;
+                for (int jb = tid - (tid & 31); jb < nvec; jb += THREADS) {
+                    const int j = jb + (tid & 31);
+                    const bool inb = j < nvec;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb) v = __ldg(std4 + j);
+                    const float s[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t k[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        has_nan |= (s[e] != s[e]);
+                        k[e] = float_to_key(s[e]);
+                        hist_add(hist, k[e] >> round_shift(0), inb);
+                    }
+                    if (inb) reinterpret_cast<uint4 *>(keys)[j] = make_uint4(k[0], k[1], k[2], k[3]);
+                }
+            } else {
+                for (int jb = tid - (tid & 31); jb < n; jb += THREADS) {
+                    const int j = jb + (tid & 31);
+                    const bool inb = j < n;
+                    const float s = inb ? __ldg(p.std + off + j) : 0.0f;
+                    has_nan |= (s != s);
+                    const uint32_t k = float_to_key(s);
+                    hist_add(hist, k >> round_shift(0), inb);
+                    if (inb) keys[j] = k;
+                }
+            }
+            if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
+            __syncthreads();
+            staged = true;
+            uint32_t lo, hi;
+            float w;
+            quantile_ranks(q, p.n, lo, hi, w);
+            uint32_t a_key, b_key;
+            block_select<THREADS>(keys, n, hist, scratch, lo, hi, true, a_key, b_key);
+            a_val = key_to_float(a_key);
+            b_val = key_to_float(b_key);
+            thr = quantile_lerp(a_val, b_val, w);
+            if (scratch[39] != 0u) thr = a_val = b_val = __int_as_float(0x7fc00000);
+        }
+        if (tid == 0) {
+            if (p.thr_out) p.thr_out[u] = thr;
+            if (p.a_out) p.a_out[u] = a_val;
+            if (p.b_out) p.b_out[u] = b_val;
+        }
+        if (p.apply_kind != 0) {
+            const float acc = apply_range<TRAIN, VEC, THREADS>(p, off, n, staged ? keys : nullptr, mode, thr, tbl_ptr, tbl64);
+            if (p.rate) {
+                const double total = block_sum_f64<THREADS>(acc, red);
+                if (tid == 0) p.rate[u] = total;
+            }
+        }
+        __syncthreads();  // keys / hist are reused by the next unit
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-CTA select rounds (large units; spatially tiled units)
+// ------------------------------------------------------------------------------------------
+__global__ void select_begin_kernel(SelectState *state, int64_t n_total, int64_t units, float q01,
+                                    const float *q01_per_unit) {
+    const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (u >= units) return;
+    SelectState st;
+    const float q = q01_per_unit ? q01_per_unit[u] : q01;
+    st.q = q;
+    st.mode = unit_mode(q);
+    st.lo = st.hi = 0;
+    st.w = 0.0f;
+    if (st.mode == kModeThreshold) quantile_ranks(q, n_total, st.lo, st.hi, st.w);
+    st.prefix = 0;
+    st.rank = st.lo;
+    st.below_total = 0;
+    st.a_key = st.b_key = 0;
+    st.need_min = 0;
+    st.nan_flag = 0;
+    st.count = 0;
+    st.pad[0] = st.pad[1] = st.pad[2] = 0;
+    state[u] = st;
+}
+
+// grid: (chunks, units).  hist: [units][kHistWords] (pre-zeroed); min_above: [units] (0xffffffff).
+template <int ROUND, bool VEC>
+__global__ void __launch_bounds__(512) hist_round_kernel(const float *std, int64_t n_local,
+                                                         const SelectState *state, uint32_t *hist,
+                                                         uint32_t *min_above) {
+    constexpr int THREADS = 512;
+    __shared__ uint32_t sh[kHistBins];
+    const int64_t u = blockIdx.y;
+    const SelectState st = state[u];
+    if (st.mode != kModeThreshold) return;
+    constexpr int shift = round_shift(ROUND);
+    constexpr int nbins = round_bins(ROUND);
+    constexpr int up = shift + (ROUND == 1 ? 11 : 10);  // bits above this round's digit
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int j = tid; j < nbins; j += THREADS) sh[j] = 0u;
+    __syncthreads();
+    const int64_t begin = static_cast<int64_t>(blockIdx.x) * kRoundChunk;
+    const int64_t end = min(n_local, begin + kRoundChunk);
+    const float *base = std + u * n_local;
+    const uint32_t want = (ROUND > 0) ? (st.prefix >> up) : 0u;
+    uint32_t mn = 0xffffffffu;
+    bool has_nan = false;
+    auto visit = [&](float s, bool inb) {
+        if (ROUND == 0) has_nan |= (inb && s != s);
+        const uint32_t k = float_to_key(s);
+        bool match = inb;
+        if (ROUND > 0) {
+            const uint32_t hb = k >> up;
+            if (ROUND == 2 && inb && hb > want) mn = min(mn, k);
+            match = inb && hb == want;
+        }
+        hist_add(sh, (k >> shift) & round_mask(ROUND), match);
+    };
+    if (VEC) {
+        const int64_t nvec = (end - begin) >> 2;  // chunk starts are multiples of 4
+        const float4 *p4 = reinterpret_cast<const float4 *>(base + begin);
+        for (int64_t jb = tid - lane; jb < nvec; jb += THREADS) {
+            const int64_t j = jb + lane;
+            const bool inb = j < nvec;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inb) v = __ldg(p4 + j);
+            visit(v.x, inb); visit(v.y, inb); visit(v.z, inb); visit(v.w, inb);
+        }
+        for (int64_t jb = begin + (nvec << 2); jb < end; jb += 32) {  // < 4 leftover elements
+            if (tid < 32) {
+                const int64_t j = jb + lane;
+                const bool inb = j < end;
+                visit(inb ? __ldg(base + j) : 0.0f, inb);
+            }
+        }
+    } else {
+        for (int64_t jb = begin + tid - lane; jb < end; jb += THREADS) {
+            const int64_t j = jb + lane;
+            const bool inb = j < end;
+            visit(inb ? __ldg(base + j) : 0.0f, inb);
+        }
+    }
+    __syncthreads();
+    uint32_t *gh = hist + u * kHistWords;
+    for (int j = tid; j < nbins; j += THREADS) {
+        const uint32_t c = sh[j];
+        if (c) atomicAdd(&gh[j], c);
+    }
+    if (ROUND == 0 && __any_sync(0xffffffffu, has_nan) && lane == 0) atomicAdd(&gh[kHistBins], 1u);
+    if (ROUND == 2) {
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (lane == 0 && mn != 0xffffffffu) atomicMin(&min_above[u], mn);
+    }
+}
+
+template <int ROUND>
+__global__ void __launch_bounds__(256) select_advance_kernel(SelectState *state, const uint32_t *hist) {
+    constexpr int THREADS = 256;
+    __shared__ uint32_t scratch[kScratchWords];
+    const int64_t u = blockIdx.x;
+    SelectState st = state[u];
+    if (st.mode != kModeThreshold) return;
+    const uint32_t *gh = hist + u * kHistWords;
+    const BinHit hit = block_find_bin<THREADS>(gh, round_bins(ROUND), st.rank, scratch);
+    st.prefix |= hit.bin << round_shift(ROUND);
+    st.rank -= hit.below;
+    st.below_total += hit.below;
+    if (ROUND == 0) st.nan_flag = gh[kHistBins];
+    if (ROUND == 2) {
+        st.a_key = st.prefix;
+        st.count = hit.count;
+        if (st.hi < st.below_total + hit.count) {
+            st.b_key = st.a_key;
+            st.need_min = 0;
+        } else {
+            const uint32_t nb = block_next_nonempty<THREADS>(gh, round_bins(2), hit.bin, scratch);
+            st.need_min = (nb == 0xffffffffu) ? 1u : 0u;
+            st.b_key = (st.prefix & ~round_mask(2)) | (nb & round_mask(2));
+        }
+    }
+    if (threadIdx.x == 0) state[u] = st;
+}
+
+__global__ void select_finish_kernel(const SelectState *state, const uint32_t *min_above,
+                                     int64_t units, float *thr_out, float *a_out, float *b_out) {
+    const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (u >= units) return;
+    const SelectState st = state[u];
+    float thr, a, b;
+    if (st.mode == kModeOnes) {
+        thr = a = b = -INFINITY;
+    } else if (st.mode == kModeZeros) {
+        thr = a = b = INFINITY;
+    } else if (st.nan_flag) {
+        thr = a = b = __int_as_float(0x7fc00000);
+    } else {
+        a = key_to_float(st.a_key);
+        b = key_to_float(st.need_min ? min_above[u] : st.b_key);
+        thr = quantile_lerp(a, b, st.w);
+    }
+    if (thr_out) thr_out[u] = thr;
+    if (a_out) a_out[u] = a;
+    if (b_out) b_out[u] = b;
+}
+
+// ------------------------------------------------------------------------------------------
+// apply with given thresholds: grid = units * tiles_per_unit
+// ------------------------------------------------------------------------------------------
+template <bool TRAIN, bool VEC>
+__global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, int tiles_per_unit) {
+    constexpr int THREADS = 256;
+    __shared__ float tbl[kTableSmem];
+    __shared__ double red[THREADS / 32];
+    const int tid = threadIdx.x;
+    const bool tbl64 = (p.table_len == kTableSmem) && p.idx;
+    if (tbl64 && tid < kTableSmem) tbl[tid] = p.table[tid];
+    if (tbl64) __syncthreads();
+    const int64_t u = blockIdx.x / tiles_per_unit;
+    const int tile = blockIdx.x - static_cast<int>(u) * tiles_per_unit;
+    const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
+    const int mode = unit_mode(q);
+    const float thr = (mode == kModeThreshold) ? p.thr_in[u] : ((mode == kModeOnes) ? -INFINITY : INFINITY);
+    if (tile == 0 && tid == 0 && p.thr_out) p.thr_out[u] = thr;
+    const int64_t begin = static_cast<int64_t>(tile) * kApplyTile;
+    const int len = static_cast<int>(min(static_cast<int64_t>(kApplyTile), p.n - begin));
+    const float acc = apply_range<TRAIN, VEC, THREADS>(p, u * p.n + begin, len, nullptr, mode, thr,
+                                                      tbl64 ? tbl : p.table, tbl64);
+    if (p.rate) {
+        const double total = block_sum_f64<THREADS>(acc, red);
+        if (tid == 0) atomicAdd(&p.rate[u], total);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of the slice
+// ------------------------------------------------------------------------------------------
+struct BwdParams {
+    const float *g_lik, *g_yhat, *y_top, *y_base, *mu, *std, *mask, *noise;
+    float scale_bound, lik_bound;
+    int64_t n;
+    float *g_ytop, *g_ybase, *g_mu, *g_std;
+};
+
+template <bool TRAIN>
+__device__ __forceinline__ void backward_one(const BwdParams &p, float gl, float gy, float yt, float yb,
+                                             float mu, float s, float m, float nz, float &g_d,
+                                             float &g_mu, float &g_s) {
+    const float r = p.y_base ? __fsub_rn(yt, yb) : yt;
+    const float d = __fsub_rn(r, mu);
+    const float y_m = __fmul_rn(d, m);
+    const float s_m = __fmul_rn(s, m);
+    const float x = TRAIN ? __fadd_rn(y_m, nz) : rintf(y_m);
+    float raw, dv, dsc;
+    likelihood_grads(x, s_m, p.scale_bound, raw, dv, dsc);
+    // likelihood LowerBound backward: pass iff raw >= bound or grad < 0
+    const float glr = (p.lik_bound > 0.0f) ? (((raw >= p.lik_bound) || (gl < 0.0f)) ? gl : 0.0f) : gl;
+    const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+    const float g_x = TRAIN ? glr * dv * sgn : 0.0f;
+    const float g_sc = glr * dsc;
+    const float g_sm = ((s_m >= p.scale_bound) || (g_sc < 0.0f)) ? g_sc : 0.0f;
+    g_d = g_x * m + gy * m;
+    g_mu = gy - g_d;
+    g_s = g_sm * m;
+}
+
+template <bool TRAIN, bool VEC>
+__global__ void __launch_bounds__(256) slice_backward_kernel(const BwdParams p) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const int64_t nvec = p.n >> 2;
+        for (int64_t j = t0; j < nvec; j += stride) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 gl = p.g_lik ? __ldg(reinterpret_cast<const float4 *>(p.g_lik) + j) : z;
+            const float4 gy = p.g_yhat ? __ldg(reinterpret_cast<const float4 *>(p.g_yhat) + j) : z;
+            const float4 yt = __ldg(reinterpret_cast<const float4 *>(p.y_top) + j);
+            const float4 yb = p.y_base ? __ldg(reinterpret_cast<const float4 *>(p.y_base) + j) : z;
+            const float4 mu = __ldg(reinterpret_cast<const float4 *>(p.mu) + j);
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(p.std) + j);
+            const float4 m = __ldg(reinterpret_cast<const float4 *>(p.mask) + j);
+            const float4 nz = TRAIN ? __ldg(reinterpret_cast<const float4 *>(p.noise) + j) : z;
+            float4 gd, gm, gs;
+            backward_one<TRAIN>(p, gl.x, gy.x, yt.x, yb.x, mu.x, s.x, m.x, nz.x, gd.x, gm.x, gs.x);
+            backward_one<TRAIN>(p, gl.y, gy.y, yt.y, yb.y, mu.y, s.y, m.y, nz.y, gd.y, gm.y, gs.y);
+            backward_one<TRAIN>(p, gl.z, gy.z, yt.z, yb.z, mu.z, s.z, m.z, nz.z, gd.z, gm.z, gs.z);
+            backward_one<TRAIN>(p, gl.w, gy.w, yt.w, yb.w, mu.w, s.w, m.w, nz.w, gd.w, gm.w, gs.w);
+            if (p.g_ytop) reinterpret_cast<float4 *>(p.g_ytop)[j] = gd;
+            if (p.g_ybase) reinterpret_cast<float4 *>(p.g_ybase)[j] = make_float4(-gd.x, -gd.y, -gd.z, -gd.w);
+            if (p.g_mu) reinterpret_cast<float4 *>(p.g_mu)[j] = gm;
+            if (p.g_std) reinterpret_cast<float4 *>(p.g_std)[j] = gs;
+        }
+    } else {
+        for (int64_t j = t0; j < p.n; j += stride) {
+            float gd, gm, gs;
+            backward_one<TRAIN>(p, p.g_lik ? p.g_lik[j] : 0.f, p.g_yhat ? p.g_yhat[j] : 0.f, p.y_top[j],
+                                p.y_base ? p.y_base[j] : 0.f, p.mu[j], p.std[j], p.mask[j],
+                                TRAIN ? p.noise[j] : 0.f, gd, gm, gs);
+            if (p.g_ytop) p.g_ytop[j] = gd;
+            if (p.g_ybase) p.g_ybase[j] = -gd;
+            if (p.g_mu) p.g_mu[j] = gm;
+            if (p.g_std) p.g_std[j] = gs;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// un-fused operators
+// ------------------------------------------------------------------------------------------
+// GaussianConditional.forward / _likelihood (entropy_models.py:620-652).
+// kind: 0 eval (round), 1 training (noise), 2 likelihood only (outputs := inputs)
+template <int KIND>
+__global__ void __launch_bounds__(256) gaussian_forward_kernel(const float *inputs, const float *scales,
+                                                               const float *means, const float *noise,
+                                                               int64_t n, float scale_bound, float lik_bound,
+                                                               float *outputs, float *lik) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float x = inputs[j];
+        const float mu = means ? means[j] : 0.0f;
+        float out;
+        if (KIND == 1) {
+            out = __fadd_rn(x, noise[j]);
+        } else if (KIND == 0) {
+            float t = means ? __fsub_rn(x, mu) : x;
+            t = rintf(t);
+            out = means ? __fadd_rn(t, mu) : t;
+        } else {
+            out = x;
+        }
+        const float value = means ? __fsub_rn(out, mu) : out;
+        if (outputs) outputs[j] = out;
+        if (lik) lik[j] = likelihood(value, scales[j], scale_bound, (KIND == 2) ? 0.0f : lik_bound);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) gaussian_backward_kernel(const float *g_out, const float *g_lik,
+                                                                const float *inputs, const float *scales,
+                                                                const float *means, const float *noise,
+                                                                int64_t n, float scale_bound, float lik_bound,
+                                                                float *g_inputs, float *g_scales, float *g_means) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float xin = inputs[j];
+        const float mu = means ? means[j] : 0.0f;
+        float out;
+        if (KIND == 1) out = __fadd_rn(xin, noise[j]);
+        else if (KIND == 0) {
+            float t = means ? __fsub_rn(xin, mu) : xin;
+            t = rintf(t);
+            out = means ? __fadd_rn(t, mu) : t;
+        } else out = xin;
+        const float x = means ? __fsub_rn(out, mu) : out;
+        const float sraw = scales[j];
+        float raw, dv, dsc;
+        likelihood_grads(x, sraw, scale_bound, raw, dv, dsc);
+        const float gl = g_lik ? g_lik[j] : 0.0f;
+        const float lb = (KIND == 2) ? 0.0f : lik_bound;
+        const float glr = (lb > 0.0f) ? (((raw >= lb) || (gl < 0.0f)) ? gl : 0.0f) : gl;
+        const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+        const float g_x = glr * dv * sgn;       // grad wrt values = outputs - means
+        const float g_sc = glr * dsc;
+        const float go = g_out ? g_out[j] : 0.0f;
+        const float g_outputs = go + g_x;
+        // outputs: noise/identity -> d/dinputs = 1 ; eval -> round() blocks inputs, d/dmeans = 1
+        if (g_inputs) g_inputs[j] = (KIND == 0) ? 0.0f : g_outputs;
+        if (g_means) g_means[j] = ((KIND == 0) ? g_outputs : 0.0f) - g_x;
+        if (g_scales) g_scales[j] = ((sraw >= scale_bound) || (g_sc < 0.0f)) ? g_sc : 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) build_indexes_kernel(const float *scales, int64_t n, const float *table,
+                                                            int table_len, float scale_bound, int32_t *idx) {
+    __shared__ float tbl[kTableSmem];
+    const bool tbl64 = table_len == kTableSmem;
+    if (tbl64 && threadIdx.x < kTableSmem) tbl[threadIdx.x] = table[threadIdx.x];
+    __syncthreads();
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float s = scales[j];
+        idx[j] = tbl64 ? scale_index64(s, scale_bound, tbl) : scale_index(s, scale_bound, table, table_len);
+    }
+}
+
+__global__ void __launch_bounds__(256) quantize_kernel(const float *inputs, const float *means, const float *noise,
+                                                       const float *mask, int64_t n, int mode, float *out_f,
+                                                       int32_t *out_i) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float x = inputs[j];
+        if (mode == PIC_QUANTIZE_NOISE) {
+            const float nz = mask ? __fmul_rn(noise[j], mask[j]) : noise[j];
+            out_f[j] = __fadd_rn(x, nz);
+            continue;
+        }
+        if (mode == PIC_QUANTIZE_STE) {
+            out_f[j] = __fadd_rn(__fsub_rn(rintf(x), x), x);
+            continue;
+        }
+        float t = means ? __fsub_rn(x, means[j]) : x;
+        t = rintf(t);
+        if (mode == PIC_QUANTIZE_DEQUANTIZE) out_f[j] = means ? __fadd_rn(t, means[j]) : t;
+        else out_i[j] = __float2int_rn(t);
+    }
+}
+
+__global__ void __launch_bounds__(256) dequantize_kernel(const int32_t *symbols, const float *means, int64_t n,
+                                                         float *out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const float v = static_cast<float>(symbols[j]);
+        out[j] = means ? __fadd_rn(v, means[j]) : v;
+    }
+}
+
+__global__ void __launch_bounds__(256) mask_from_threshold_kernel(const float *std, const float *thr,
+                                                                  int64_t n_per_unit, int64_t total,
+                                                                  float *mask) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < total; j += stride) {
+        const float t = thr[j / n_per_unit];
+        mask[j] = (std[j] >= t) ? 1.0f : 0.0f;
+    }
+}
+
+// per-unit sum ln(x): grid (chunks, units), atomics in f64 (out pre-zeroed)
+__global__ void __launch_bounds__(256) log_sum_kernel(const float *x, int64_t n_per_unit, double *out) {
+    __shared__ double red[8];
+    const int64_t u = blockIdx.y;
+    const float *base = x + u * n_per_unit;
+    float acc = 0.0f;
+    int cnt = 0;
+    double dacc = 0.0;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n_per_unit;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        acc += logf(base[j]);
+        if (++cnt == 64) { dacc += acc; acc = 0.0f; cnt = 0; }
+    }
+    dacc += acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_down_sync(0xffffffffu, dacc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(&out[u], t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------
+static size_t fused_smem_bytes(int64_t n) {
+    const int64_t n_pad = (n + 3) & ~int64_t(3);
+    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kScratchWords * 4 + kTableSmem * 4 + 32 * 8;
+}
+
+template <bool TRAIN, bool VEC, int THREADS>
+static int launch_fused_t(const SliceParams &p, cudaStream_t stream) {
+    const size_t smem = fused_smem_bytes(p.n);
+    auto kern = slice_fused_kernel<TRAIN, VEC, THREADS>;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        configured = 232448;
+    }
+    static size_t occ_smem = ~size_t(0);
+    static int occ_blocks = 1;
+    if (smem != occ_smem) {
+        int q = 1;
+        PIC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));
+        occ_blocks = q < 1 ? 1 : q;
+        occ_smem = smem;
+    }
+    const int per_sm = occ_blocks;
+    const int64_t max_grid = static_cast<int64_t>(sm_count()) * per_sm;
+    const int grid = static_cast<int>(p.units < max_grid ? p.units : max_grid);
+    kern<<<grid, THREADS, smem, stream>>>(p);
+    return launch_status();
+}
+
+template <bool TRAIN, bool VEC>
+static int launch_fused_v(const SliceParams &p, cudaStream_t stream) {
+    if (p.n > 16384) return launch_fused_t<TRAIN, VEC, 1024>(p, stream);
+    if (p.n > 4096) return launch_fused_t<TRAIN, VEC, 512>(p, stream);
+    return launch_fused_t<TRAIN, VEC, 256>(p, stream);
+}
+
+static bool slice_vec_ok(const SliceParams &p) {
+    if (p.n % 4 != 0) return false;
+    const void *ptrs[] = {p.y_top, p.y_base, p.mu, p.std, p.noise, p.mask, p.y_hat, p.lik, p.idx, p.symbols};
+    for (const void *q : ptrs)
+        if (q && !aligned16(q)) return false;
+    return true;
+}
+
+static int launch_fused(const SliceParams &p, cudaStream_t stream) {
+    const bool vec = slice_vec_ok(p);
+    const bool train = p.noise != nullptr && p.apply_kind == 2;
+    if (train) return vec ? launch_fused_v<true, true>(p, stream) : launch_fused_v<true, false>(p, stream);
+    return vec ? launch_fused_v<false, true>(p, stream) : launch_fused_v<false, false>(p, stream);
+}
+
+static int launch_apply(const SliceParams &p, cudaStream_t stream) {
+    const bool vec = slice_vec_ok(p);
+    const bool train = p.noise != nullptr && p.apply_kind == 2;
+    const int tiles = static_cast<int>((p.n + kApplyTile - 1) / kApplyTile);
+    const int64_t grid64 = p.units * tiles;
+    if (grid64 > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
+    const int grid = static_cast<int>(grid64);
+    if (p.rate) PIC_CUDA_CHECK(cudaMemsetAsync(p.rate, 0, sizeof(double) * p.units, stream));
+    if (train) {
+        if (vec) slice_apply_kernel<true, true><<<grid, 256, 0, stream>>>(p, tiles);
+        else slice_apply_kernel<true, false><<<grid, 256, 0, stream>>>(p, tiles);
+    } else {
+        if (vec) slice_apply_kernel<false, true><<<grid, 256, 0, stream>>>(p, tiles);
+        else slice_apply_kernel<false, false><<<grid, 256, 0, stream>>>(p, tiles);
+    }
+    return launch_status();
+}
+
+// workspace layout of the multi-launch select: [state][hist x3 rounds][min_above]
+struct RoundsWs {
+    SelectState *state;
+    uint32_t *hist[3];
+    uint32_t *min_above;
+    float *thr;
+};
+
+static size_t rounds_ws_bytes(int64_t units) {
+    size_t b = 0;
+    b += static_cast<size_t>(units) * sizeof(SelectState);
+    b += static_cast<size_t>(units) * kHistWords * 4 * 3;
+    b += ((static_cast<size_t>(units) * 4 + 63) / 64) * 64;  // min_above
+    b += ((static_cast<size_t>(units) * 4 + 63) / 64) * 64;  // thr
+    return b;
+}
+
+static RoundsWs carve_ws(void *ws, int64_t units) {
+    RoundsWs r;
+    unsigned char *p = static_cast<unsigned char *>(ws);
+    r.state = reinterpret_cast<SelectState *>(p);
+    p += static_cast<size_t>(units) * sizeof(SelectState);
+    for (int i = 0; i < 3; ++i) {
+        r.hist[i] = reinterpret_cast<uint32_t *>(p);
+        p += static_cast<size_t>(units) * kHistWords * 4;
+    }
+    r.min_above = reinterpret_cast<uint32_t *>(p);
+    p += ((static_cast<size_t>(units) * 4 + 63) / 64) * 64;
+    r.thr = reinterpret_cast<float *>(p);
+    return r;
+}
+
+static int launch_hist_round(const float *std, int64_t n_local, int64_t units, int round,
+                             const SelectState *state, uint32_t *hist, uint32_t *min_above,
+                             cudaStream_t stream) {
+    if (units > 65535) return PIC_ERR_TOO_LARGE;
+    PIC_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(units) * kHistWords * 4, stream));
+    if (round == 2) PIC_CUDA_CHECK(cudaMemsetAsync(min_above, 0xff, static_cast<size_t>(units) * 4, stream));
+    if (n_local == 0) return PIC_OK;
+    const bool vec = (n_local % 4 == 0) && aligned16(std);
+    dim3 grid(static_cast<unsigned>((n_local + kRoundChunk - 1) / kRoundChunk), static_cast<unsigned>(units));
+#define PIC_LAUNCH_ROUND(R)                                                                                  \
+    if (vec) hist_round_kernel<R, true><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above);      \
+    else hist_round_kernel<R, false><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above)
+    if (round == 0) { PIC_LAUNCH_ROUND(0); }
+    else if (round == 1) { PIC_LAUNCH_ROUND(1); }
+    else { PIC_LAUNCH_ROUND(2); }
+#undef PIC_LAUNCH_ROUND
+    return launch_status();
+}
+
+static int launch_advance(SelectState *state, const uint32_t *hist, int64_t units, int round,
+                          cudaStream_t stream) {
+    const unsigned grid = static_cast<unsigned>(units);
+    if (round == 0) select_advance_kernel<0><<<grid, 256, 0, stream>>>(state, hist);
+    else if (round == 1) select_advance_kernel<1><<<grid, 256, 0, stream>>>(state, hist);
+    else select_advance_kernel<2><<<grid, 256, 0, stream>>>(state, hist);
+    return launch_status();
+}
+
+// full multi-launch select on one device
+static int select_rounds(const float *std, int64_t n, int64_t units, float q01, const float *q01_per_unit,
+                         float *thr_out, float *a_out, float *b_out, void *ws, cudaStream_t stream) {
+    RoundsWs w = carve_ws(ws, units);
+    select_begin_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, n, units, q01, q01_per_unit);
+    int rc = launch_status();
+    for (int r = 0; r < 3 && rc == PIC_OK; ++r) {
+        rc = launch_hist_round(std, n, units, r, w.state, w.hist[r], w.min_above, stream);
+        if (rc == PIC_OK) rc = launch_advance(w.state, w.hist[r], units, r, stream);
+    }
+    if (rc != PIC_OK) return rc;
+    select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
+                                                                                      thr_out, a_out, b_out);
+    return launch_status();
+}
+
+static int check_common(int64_t n_per_unit, int64_t units) {
+    if (n_per_unit <= 0 || units <= 0) return PIC_ERR_INVALID_ARGUMENT;
+    if (n_per_unit > (int64_t(1) << 24)) return PIC_ERR_TOO_LARGE;
+    return PIC_OK;
+}
+
+static int elementwise_grid(int64_t n, int per_thread = 4) {
+    const int64_t blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    const int64_t g = blocks < cap ? blocks : cap;
+    return static_cast<int>(g < 1 ? 1 : g);
+}
+
+}  // namespace pic
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace pic;
+
+extern "C" {
+
+int pic_version(void) { return 100; }
+
+const char *pic_error_string(int code) {
+    switch (code) {
+        case PIC_OK: return "ok";
+        case PIC_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case PIC_ERR_TOO_LARGE: return "quantile() input tensor is too large";
+        case PIC_ERR_WORKSPACE: return "workspace too small";
+        case PIC_ERR_CUDA: return "CUDA runtime error";
+        case PIC_ERR_UNALIGNED: return "pointer is not 4-byte aligned";
+        default: return "unknown error";
+    }
+}
+
+int pic_last_cuda_error(void) { return g_last_cuda_error; }
+
+int64_t pic_fused_max_elems(void) { return kFusedMaxElems; }
+
+size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units) {
+    if (n_per_unit <= kFusedMaxElems || units <= 0) return 256;  // fused path needs none; keep non-zero
+    return rounds_ws_bytes(units);
+}
+
+size_t pic_select_state_bytes(int64_t units) { return static_cast<size_t>(units < 1 ? 1 : units) * sizeof(SelectState); }
+int64_t pic_hist_words(void) { return kHistWords; }
+
+int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, float q01,
+                         const float *q01_per_unit, float *thr_out, float *a_out, float *b_out,
+                         void *ws, size_t ws_bytes, pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!std || !thr_out) return PIC_ERR_INVALID_ARGUMENT;
+    if (!aligned4(std)) return PIC_ERR_UNALIGNED;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_per_unit <= kFusedMaxElems) {
+        SliceParams p{};
+        p.std = std; p.q01 = q01; p.q01_per_unit = q01_per_unit;
+        p.n = n_per_unit; p.units = units;
+        p.thr_out = thr_out; p.a_out = a_out; p.b_out = b_out;
+        p.apply_kind = 0;
+        return launch_fused(p, stream);
+    }
+    if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
+    return select_rounds(std, n_per_unit, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
+}
+
+int pic_select_begin(void *state, int64_t n_total, int64_t units, float q01, const float *q01_per_unit,
+                     pic_stream_t stream_) {
+    int rc = check_common(n_total, units);
+    if (rc != PIC_OK) return rc;
+    if (!state) return PIC_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    select_begin_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(
+        static_cast<SelectState *>(state), n_total, units, q01, q01_per_unit);
+    return launch_status();
+}
+
+int pic_hist_round(const float *std_local, int64_t n_local, int64_t units, int round, const void *state,
+                   uint32_t *hist, uint32_t *min_above, pic_stream_t stream_) {
+    if (round < 0 || round > 2 || units <= 0 || n_local < 0 || !state || !hist) return PIC_ERR_INVALID_ARGUMENT;
+    if (round == 2 && !min_above) return PIC_ERR_INVALID_ARGUMENT;
+    if (n_local > 0 && !std_local) return PIC_ERR_INVALID_ARGUMENT;
+    return launch_hist_round(std_local, n_local, units, round, static_cast<const SelectState *>(state), hist,
+                             min_above, static_cast<cudaStream_t>(stream_));
+}
+
+int pic_select_advance(void *state, const uint32_t *hist, int64_t units, int round, pic_stream_t stream_) {
+    if (round < 0 || round > 2 || units <= 0 || !state || !hist) return PIC_ERR_INVALID_ARGUMENT;
+    return launch_advance(static_cast<SelectState *>(state), hist, units, round, static_cast<cudaStream_t>(stream_));
+}
+
+int pic_select_finish(const void *state, const uint32_t *min_above, int64_t units, float *thr_out, float *a_out,
+                      float *b_out, pic_stream_t stream_) {
+    if (units <= 0 || !state || !min_above || !thr_out) return PIC_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(
+        static_cast<const SelectState *>(state), min_above, units, thr_out, a_out, b_out);
+    return launch_status();
+}
+
+int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float q01, const float *q01_per_unit,
+                     float *mask, float *thr_out, void *ws, size_t ws_bytes, pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!std || !mask) return PIC_ERR_INVALID_ARGUMENT;
+    if (!aligned4(std) || !aligned4(mask)) return PIC_ERR_UNALIGNED;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SliceParams p{};
+    p.std = std; p.q01 = q01; p.q01_per_unit = q01_per_unit;
+    p.n = n_per_unit; p.units = units;
+    p.mask = mask; p.thr_out = thr_out;
+    p.apply_kind = 1;
+    const bool needs_select = q01_per_unit || unit_mode(q01) == kModeThreshold;
+    if (n_per_unit <= kFusedMaxElems) return launch_fused(p, stream);
+    if (needs_select) {
+        if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
+        RoundsWs w = carve_ws(ws, units);
+        rc = select_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, stream);
+        if (rc != PIC_OK) return rc;
+        p.thr_in = w.thr;
+    }
+    return launch_apply(p, stream);
+}
+
+int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_unit, int64_t units, float *mask,
+                            pic_stream_t stream_) {
+    if (n_per_unit <= 0 || units <= 0 || !std || !thr || !mask) return PIC_ERR_INVALID_ARGUMENT;
+    const int64_t total = n_per_unit * units;
+    mask_from_threshold_kernel<<<elementwise_grid(total), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        std, thr, n_per_unit, total, mask);
+    return launch_status();
+}
+
+int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, const float *std, float q01,
+                      const float *q01_per_unit, const float *thr_in, const float *noise,
+                      const float *scale_table, int table_len, float scale_bound, float lik_bound,
+                      int64_t n_per_unit, int64_t units, float *mask, float *y_hat, float *lik, int32_t *idx,
+                      int32_t *symbols, float *thr_out, double *rate, void *ws, size_t ws_bytes,
+                      pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!y_top || !mu || !std) return PIC_ERR_INVALID_ARGUMENT;
+    if (idx && (!scale_table || table_len < 1)) return PIC_ERR_INVALID_ARGUMENT;
+    if (!(scale_bound > 0.0f)) return PIC_ERR_INVALID_ARGUMENT;
+    const void *ptrs[] = {y_top, y_base, mu, std, noise, mask, y_hat, lik, idx, symbols};
+    for (const void *q : ptrs)
+        if (q && !aligned4(q)) return PIC_ERR_UNALIGNED;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SliceParams p{};
+    p.y_top = y_top; p.y_base = y_base; p.mu = mu; p.std = std;
+    p.q01 = q01; p.q01_per_unit = q01_per_unit; p.thr_in = thr_in; p.noise = noise;
+    p.table = scale_table; p.table_len = table_len;
+    p.scale_bound = scale_bound; p.lik_bound = lik_bound;
+    p.n = n_per_unit; p.units = units;
+    p.mask = mask; p.y_hat = y_hat; p.lik = lik; p.idx = idx; p.symbols = symbols;
+    p.thr_out = thr_out; p.rate = rate;
+    p.apply_kind = 2;
+    if (n_per_unit <= kFusedMaxElems) return launch_fused(p, stream);
+    const bool needs_select = !thr_in && (q01_per_unit || unit_mode(q01) == kModeThreshold);
+    if (needs_select) {
+        if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
+        RoundsWs w = carve_ws(ws, units);
+        rc = select_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, stream);
+        if (rc != PIC_OK) return rc;
+        p.thr_in = w.thr;
+    }
+    return launch_apply(p, stream);
+}
+
+int pic_slice_backward(const float *g_lik, const float *g_yhat, const float *y_top, const float *y_base,
+                       const float *mu, const float *std, const float *mask, const float *noise,
+                       float scale_bound, float lik_bound, int64_t n, float *g_ytop, float *g_ybase, float *g_mu,
+                       float *g_std, pic_stream_t stream_) {
+    if (n <= 0 || !y_top || !mu || !std || !mask) return PIC_ERR_INVALID_ARGUMENT;
+    BwdParams p{g_lik, g_yhat, y_top, y_base, mu, std, mask, noise, scale_bound, lik_bound, n,
+                g_ytop, g_ybase, g_mu, g_std};
+    const void *ptrs[] = {g_lik, g_yhat, y_top, y_base, mu, std, mask, noise, g_ytop, g_ybase, g_mu, g_std};
+    bool vec = (n % 4 == 0);
+    for (const void *q : ptrs) {
+        if (q && !aligned4(q)) return PIC_ERR_UNALIGNED;
+        if (q && !aligned16(q)) vec = false;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int grid = elementwise_grid(n, 4);
+    if (noise) {
+        if (vec) slice_backward_kernel<true, true><<<grid, 256, 0, stream>>>(p);
+        else slice_backward_kernel<true, false><<<grid, 256, 0, stream>>>(p);
+    } else {
+        if (vec) slice_backward_kernel<false, true><<<grid, 256, 0, stream>>>(p);
+        else slice_backward_kernel<false, false><<<grid, 256, 0, stream>>>(p);
+    }
+    return launch_status();
+}
+
+int pic_gaussian_forward(const float *inputs, const float *scales, const float *means, const float *noise,
+                         int likelihood_only, int64_t n, float scale_bound, float lik_bound, float *outputs,
+                         float *lik, pic_stream_t stream_) {
+    if (n <= 0 || !inputs || !scales) return PIC_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int grid = elementwise_grid(n, 2);
+    if (likelihood_only) gaussian_forward_kernel<2><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
+    else if (noise) gaussian_forward_kernel<1><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
+    else gaussian_forward_kernel<0><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
+    return launch_status();
+}
+
+int pic_gaussian_backward(const float *g_out, const float *g_lik, const float *inputs, const float *scales,
+                          const float *means, const float *noise, int likelihood_only, int64_t n,
+                          float scale_bound, float lik_bound, float *g_inputs, float *g_scales, float *g_means,
+                          pic_stream_t stream_) {
+    if (n <= 0 || !inputs || !scales) return PIC_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int grid = elementwise_grid(n, 2);
+    if (likelihood_only) gaussian_backward_kernel<2><<<grid, 256, 0, stream>>>(g_out, g_lik, inputs, scales, means, noise, n, scale_bound, lik_bound, g_inputs, g_scales, g_means);
+    else if (noise) gaussian_backward_kernel<1><<<grid, 256, 0, stream>>>(g_out, g_lik, inputs, scales, means, noise, n, scale_bound, lik_bound, g_inputs, g_scales, g_means);
+    else gaussian_backward_kernel<0><<<grid, 256, 0, stream>>>(g_out, g_lik, inputs, scales, means, noise, n, scale_bound, lik_bound, g_inputs, g_scales, g_means);
+    return launch_status();
+}
+
+int pic_build_indexes(const float *scales, int64_t n, const float *scale_table, int table_len, float scale_bound,
+                      int32_t *idx, pic_stream_t stream_) {
+    if (n <= 0 || !scales || !scale_table || table_len < 1 || !idx) return PIC_ERR_INVALID_ARGUMENT;
+    build_indexes_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        scales, n, scale_table, table_len, scale_bound, idx);
+    return launch_status();
+}
+
+int pic_quantize(const float *inputs, const float *means, const float *noise, const float *mask, int64_t n,
+                 int mode, float *out_f32, int32_t *out_i32, pic_stream_t stream_) {
+    if (mode < 0 || mode > 3) return PIC_ERR_INVALID_ARGUMENT;  // ValueError in the reference
+    if (n <= 0 || !inputs) return PIC_ERR_INVALID_ARGUMENT;
+    if (mode == PIC_QUANTIZE_NOISE && (!noise || !out_f32)) return PIC_ERR_INVALID_ARGUMENT;
+    if ((mode == PIC_QUANTIZE_DEQUANTIZE || mode == PIC_QUANTIZE_STE) && !out_f32) return PIC_ERR_INVALID_ARGUMENT;
+    if (mode == PIC_QUANTIZE_SYMBOLS && !out_i32) return PIC_ERR_INVALID_ARGUMENT;
+    quantize_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(inputs, means, noise, mask, n,
+                                                                                      mode, out_f32, out_i32);
+    return launch_status();
+}
+
+int pic_dequantize(const int32_t *symbols, const float *means, int64_t n, float *out, pic_stream_t stream_) {
+    if (n <= 0 || !symbols || !out) return PIC_ERR_INVALID_ARGUMENT;
+    dequantize_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(symbols, means, n, out);
+    return launch_status();
+}
+
+int pic_log_sum(const float *x, int64_t n_per_unit, int64_t units, double *out, pic_stream_t stream_) {
+    if (n_per_unit <= 0 || units <= 0 || units > 65535 || !x || !out) return PIC_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PIC_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * units, stream));
+    int chunks = static_cast<int>((n_per_unit + 256 * 16 - 1) / (256 * 16));
+    const int cap = (sm_count() * 8 + static_cast<int>(units) - 1) / static_cast<int>(units);
+    if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+    log_sum_kernel<<<dim3(chunks, static_cast<unsigned>(units)), 256, 0, stream>>>(x, n_per_unit, out);
+    return launch_status();
+}
+
+}  // extern "C"

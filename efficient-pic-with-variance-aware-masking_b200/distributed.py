@@ -1,0 +1,111 @@
+"""Multi-GPU forms of the path.  One process per GPU, torch.distributed for plumbing.
+
+* Batch sharding (BASELINE configs 3/4): units are independent -- ``shard_range`` gives each
+  rank its slice of the image batch; the path needs NO data-path collective.
+* Spatial tiling (config 5, one huge image): every rank holds a band of each unit's latent.
+  Everything is elementwise except the per-unit threshold, which needs global order
+  statistics: per radix round (11/11/10 key bits) each rank histograms its tile
+  (pic_hist_round), the histograms are all-reduced (sum, 2056 uint32 words per unit -- a
+  latency-bound NCCL message over NVLink/NVSwitch), every rank advances the same state
+  (pic_select_advance); one more all-reduce (min) supplies the successor key when it lies
+  outside the final bucket.  All ranks then hold bit-identical thresholds and apply them
+  locally (pic_slice_forward with thr_in), so masks equal the single-GPU / CPU result.
+
+The local kernels sit behind a small backend interface so the collective protocol can be
+exercised on CPU with gloo in the test-suite (tests inject a numpy backend; the product
+backend is CUDA-only).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import check, lib
+
+_SIGN = -(2 ** 31)
+
+
+def shard_range(total_units: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of the unit batch owned by `rank` (sizes differ by <= 1)."""
+    base, rem = divmod(total_units, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class CudaTileBackend:
+    """Local steps of the tiled select on this rank's CUDA tile (C ABI section 1b)."""
+
+    def __init__(self, std_local: torch.Tensor, units: int):
+        self.std = ops._require(std_local, "std_local")
+        self.units = units
+        self.n_local = self.std.numel() // units if units else 0
+        dev = self.std.device
+        self.state = torch.empty(int(lib().pic_select_state_bytes(units)), dtype=torch.uint8, device=dev)
+        self.words = int(lib().pic_hist_words())
+        self.hist = torch.empty(units * self.words, dtype=torch.int32, device=dev)
+        self.min_above = torch.empty(units, dtype=torch.int32, device=dev)
+
+    def begin(self, n_total: int, q01) -> None:
+        q, qt = ops._q_args(q01, self.units, self.std.device)
+        check(lib().pic_select_begin(self.state.data_ptr(), n_total, self.units, q, ops._ptr(qt), ops._stream()),
+              "pic_select_begin")
+
+    def hist_round(self, rnd: int) -> torch.Tensor:
+        check(lib().pic_hist_round(self.std.data_ptr(), self.n_local, self.units, rnd, self.state.data_ptr(),
+                                   self.hist.data_ptr(), self.min_above.data_ptr(), ops._stream()), "pic_hist_round")
+        return self.hist
+
+    def advance(self, hist: torch.Tensor, rnd: int) -> None:
+        check(lib().pic_select_advance(self.state.data_ptr(), hist.data_ptr(), self.units, rnd, ops._stream()),
+              "pic_select_advance")
+
+    def min_above_keys(self) -> torch.Tensor:
+        return self.min_above
+
+    def finish(self, min_above: torch.Tensor) -> torch.Tensor:
+        thr = torch.empty(self.units, dtype=torch.float32, device=self.std.device)
+        check(lib().pic_select_finish(self.state.data_ptr(), min_above.data_ptr(), self.units, thr.data_ptr(),
+                                      None, None, ops._stream()), "pic_select_finish")
+        return thr
+
+
+def allreduce_min_u32(keys_i32: torch.Tensor, group=None) -> torch.Tensor:
+    """MIN over ranks of uint32 keys stored in an int32 tensor (torch has no uint32 collectives):
+    flipping the top bit maps unsigned order onto signed order."""
+    flipped = keys_i32 ^ _SIGN
+    dist.all_reduce(flipped, op=dist.ReduceOp.MIN, group=group)
+    return flipped ^ _SIGN
+
+
+def tiled_select_threshold(std_local: Optional[torch.Tensor], units: int, n_total: int, q01, group=None,
+                           backend=None) -> torch.Tensor:
+    """Global per-unit quantile threshold of units whose elements are spread over the ranks of
+    `group`.  Returns thr [units], bit-identical on every rank."""
+    be = backend if backend is not None else CudaTileBackend(std_local, units)
+    be.begin(n_total, q01)
+    for rnd in range(3):
+        hist = be.hist_round(rnd)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)  # counts < 2^24: int32 view is exact
+        be.advance(hist, rnd)
+    mn = allreduce_min_u32(be.min_above_keys(), group)
+    return be.finish(mn)
+
+
+def tiled_slice_forward(y_top, y_base, mu, std, units: int, n_total: int, pr, scale_table=None, noise=None,
+                        group=None, scale_bound: float = 0.11, lik_bound: float = 1e-9,
+                        want=("mask", "y_hat", "lik")) -> dict:
+    """One progressive slice of spatially tiled units: all-reduced threshold + local apply."""
+    q01 = pr if isinstance(pr, torch.Tensor) else ops.pr_to_q01(pr)
+    mode_scalar = None if isinstance(q01, torch.Tensor) else q01
+    if mode_scalar is not None and not (0.0 <= mode_scalar <= 1.0):
+        # ones / zeros short-circuit: no threshold, no collective
+        return ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise,
+                                 scale_bound=scale_bound, lik_bound=lik_bound, want=want)
+    thr = tiled_select_threshold(std, units, n_total, q01, group)
+    res = ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise, thr_in=thr,
+                            scale_bound=scale_bound, lik_bound=lik_bound, want=want)
+    res["thr"] = thr
+    return res

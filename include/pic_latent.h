@@ -1,0 +1,195 @@
+/*
+ * pic_latent.h -- C ABI of libpic_latent.so: the B200 (sm_100a) implementation of the
+ * latent-side hot path of the PIC / REM progressive image codec
+ * (reference: das-ankur/Efficient-PIC-with-Variance-Aware-Masking, paths below are
+ * relative to its src/ directory).
+ *
+ * The reference has no FFI: its boundary for this path is the Python method surface
+ *   layers/channel_mask.py:9-156      ChannelMask.{forward, ProgMask, apply_noise}, ste_round
+ *   entropy_models/entropy_models.py  EntropyModel.{quantize 127-153, dequantize 161-168},
+ *                                     GaussianConditional.{_likelihood 620-635, forward 637-652,
+ *                                     build_indexes 654-659}
+ *   models/pic.py:401-402,430-443,583-584,621-629,809-820,945-948  (per-slice glue)
+ *   training/loss.py:45-60            (rate reduction)
+ * Each entry point below names the reference lines it replaces.  The Python drop-in classes
+ * (efficient-pic-with-variance-aware-masking_b200/) bind these symbols with ctypes; a
+ * maintainer of the reference would bind them the same way.
+ *
+ * Conventions
+ *  - All tensor pointers are caller-owned DEVICE memory on the current CUDA device, dense
+ *    f32/i32, laid out as `units` consecutive blocks of `n_per_unit` elements.  A *unit* is
+ *    one (image, progressive slice) block [32,h,w] of a contiguous NCHW tensor [B,32,h,w],
+ *    i.e. n_per_unit = 32*h*w and units = B (times slices when slices are batched).
+ *  - Every call is asynchronous on `stream` (a cudaStream_t), never synchronises the host,
+ *    never allocates, keeps no state between calls and is CUDA-graph capturable.  Scratch
+ *    memory is passed in (`ws`, size from the matching *_workspace_bytes()).
+ *  - Inputs are never modified.  Nullable pointers are marked; a NULL output is skipped.
+ *  - Quantile control: `q01` is the f32 torch.quantile argument 1 - min(pr,10)*0.1
+ *    (channel_mask.py:138-140).  Values outside [0,1] select the reference's
+ *    short-circuits: q01 < 0  => all-ones mask (pr >= 10, channel_mask.py:133-134),
+ *                    q01 > 1  => all-zeros mask (pr == 0, channel_mask.py:135-136).
+ *    `q01_per_unit` (device, nullable) overrides the scalar `q01` with one value per unit.
+ *  - Return value: PIC_OK or a negative PIC_ERR_* code; nothing throws.
+ */
+#ifndef PIC_LATENT_H_
+#define PIC_LATENT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIC_OK 0
+#define PIC_ERR_INVALID_ARGUMENT (-1) /* ValueError / NotImplementedError in the reference API   */
+#define PIC_ERR_TOO_LARGE (-2)        /* torch.quantile: "input tensor is too large" (n > 2^24)   */
+#define PIC_ERR_WORKSPACE (-3)        /* ws_bytes smaller than *_workspace_bytes()               */
+#define PIC_ERR_CUDA (-4)             /* a CUDA runtime call failed: see pic_last_cuda_error()    */
+#define PIC_ERR_UNALIGNED (-5)        /* pointer not 4-byte aligned                              */
+
+#define PIC_Q_ONES (-1.0f) /* q01 sentinel: pr >= 10 */
+#define PIC_Q_ZEROS (2.0f) /* q01 sentinel: pr == 0  */
+
+#define PIC_QUANTIZE_NOISE 0      /* entropy_models.py:132-138 */
+#define PIC_QUANTIZE_DEQUANTIZE 1 /* entropy_models.py:140-149 */
+#define PIC_QUANTIZE_SYMBOLS 2    /* entropy_models.py:151-153 */
+#define PIC_QUANTIZE_STE 3        /* ste_round forward: round(x) - x + x (channel_mask.py:5-6) */
+
+typedef void *pic_stream_t; /* cudaStream_t */
+
+int pic_version(void);
+const char *pic_error_string(int code);
+int pic_last_cuda_error(void); /* cudaError_t of the last failing runtime call on this thread */
+
+/* Largest n_per_unit served by the single-launch fused kernel (std tile of the unit staged in
+ * shared memory between select and apply); larger units take the multi-launch path. */
+int64_t pic_fused_max_elems(void);
+
+/* Scratch needed by pic_select_threshold / pic_channel_mask / pic_slice_forward. */
+size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units);
+
+/*
+ * (1) Threshold selection: exact torch.quantile(std[u].ravel(), q01, interpolation="linear")
+ * per unit (channel_mask.py:41,145; ATen quantile semantics: f32 rank = q01*f32(n-1),
+ * a = sorted[floor], b = sorted[ceil], FMA lerp; any NaN => NaN).  For the q01 sentinels
+ * thr_out is -inf (ones) / +inf (zeros).  a_out / b_out (nullable) receive the two order
+ * statistics.
+ */
+int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, float q01,
+                         const float *q01_per_unit, float *thr_out, float *a_out, float *b_out,
+                         void *ws, size_t ws_bytes, pic_stream_t stream);
+
+/*
+ * (1b) Split form of (1) for spatially tiled units (one image sharded over several GPUs,
+ * SURVEY 8e).  Radix rounds r = 0,1,2 (11/11/10 key bits).  Per round every rank calls
+ * pic_hist_round() on its local tile, all-reduces `hist` (uint32 sum, pic_hist_words() words
+ * per unit) and calls pic_select_advance(); after round 2 ranks all-reduce `min_above`
+ * (uint32 min, one word per unit) and call pic_select_finish().  `state` is
+ * pic_select_state_bytes(units) bytes of device memory owned by the caller; n_total is the
+ * element count of the whole (global) unit.
+ */
+size_t pic_select_state_bytes(int64_t units);
+int64_t pic_hist_words(void);
+int pic_select_begin(void *state, int64_t n_total, int64_t units, float q01,
+                     const float *q01_per_unit, pic_stream_t stream);
+int pic_hist_round(const float *std_local, int64_t n_local, int64_t units, int round,
+                   const void *state, uint32_t *hist, uint32_t *min_above, pic_stream_t stream);
+int pic_select_advance(void *state, const uint32_t *hist, int64_t units, int round,
+                       pic_stream_t stream);
+int pic_select_finish(const void *state, const uint32_t *min_above, int64_t units, float *thr_out,
+                      float *a_out, float *b_out, pic_stream_t stream);
+
+/*
+ * (2) ChannelMask.forward / ProgMask (channel_mask.py:18-49, 89-151): mask = (std >= thr) as
+ * f32 {0,1}; ones / zeros for the sentinels.  thr_out nullable.
+ */
+int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float q01,
+                     const float *q01_per_unit, float *mask, float *thr_out, void *ws,
+                     size_t ws_bytes, pic_stream_t stream);
+
+/* mask = (std >= thr[u]) with thresholds already known (e.g. all-reduced ones). */
+int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_unit,
+                            int64_t units, float *mask, pic_stream_t stream);
+
+/*
+ * (3) One progressive slice, fused (models/pic.py:583-584, 621-629 and 809-820):
+ *   r      = y_top - y_base                (y_base NULL => r = y_top, delta_encode off)
+ *   mask   = std >= thr                    (thr selected here, or taken from thr_in if non-NULL)
+ *   y_m    = (r - mu) * mask ;  s_m = std * mask
+ *   out    = noise ? y_m + noise : round(y_m)          (GaussianConditional.quantize)
+ *   lik    = max(Phi((.5-|out|)/s) - Phi((-.5-|out|)/s), lik_bound),  s = max(s_m, scale_bound)
+ *   y_hat  = round(r - mu) * mask + mu                 (ste_round forward; masked => mu)
+ *   idx    = #{t in scale_table[:-1] : t < s}          (build_indexes)
+ *   symbols= int32(round(y_m))                         (quantize(.., "symbols"))
+ *   rate[u]= sum_i ln(lik[u,i])  (f64; training/loss.py:45-60 divides by -ln2*num_pixels)
+ * Outputs mask, y_hat, lik, idx, symbols, thr_out, rate are each nullable.
+ * scale_table: device pointer to table_len sorted f32 (GaussianConditional.scale_table).
+ */
+int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, const float *std,
+                      float q01, const float *q01_per_unit, const float *thr_in,
+                      const float *noise, const float *scale_table, int table_len,
+                      float scale_bound, float lik_bound, int64_t n_per_unit, int64_t units,
+                      float *mask, float *y_hat, float *lik, int32_t *idx, int32_t *symbols,
+                      float *thr_out, double *rate, void *ws, size_t ws_bytes,
+                      pic_stream_t stream);
+
+/*
+ * (4) Backward of (3) (autograd of the same lines).  `mask` is the forward
+ * mask; g_lik / g_yhat nullable (treated as zero); g_ybase nullable.  noise NULL => eval
+ * forward (round() blocks the gradient into y_m).
+ */
+int pic_slice_backward(const float *g_lik, const float *g_yhat, const float *y_top,
+                       const float *y_base, const float *mu, const float *std,
+                       const float *mask, const float *noise, float scale_bound, float lik_bound,
+                       int64_t n, float *g_ytop, float *g_ybase, float *g_mu, float *g_std,
+                       pic_stream_t stream);
+
+/*
+ * (5) Un-fused operators, for API parity with GaussianConditional / EntropyModel.
+ *  pic_gaussian_forward : forward(inputs, scales, means, training) entropy_models.py:637-652
+ *                         (noise NULL => eval; outputs nullable => _likelihood only with
+ *                         outputs := inputs when `likelihood_only` != 0, entropy_models.py:620-635)
+ *  pic_gaussian_backward: its autograd (g_out, g_lik nullable)
+ *  pic_build_indexes    : build_indexes, entropy_models.py:654-659
+ *  pic_quantize         : quantize, entropy_models.py:127-153 (noise*mask when mask given)
+ *  pic_dequantize       : dequantize, entropy_models.py:161-168 (int32 symbols + means)
+ *  pic_log_sum          : per-unit sum ln(x) (rate numerator, training/loss.py:45-60)
+ */
+int pic_gaussian_forward(const float *inputs, const float *scales, const float *means,
+                         const float *noise, int likelihood_only, int64_t n, float scale_bound,
+                         float lik_bound, float *outputs, float *lik, pic_stream_t stream);
+int pic_gaussian_backward(const float *g_out, const float *g_lik, const float *inputs,
+                          const float *scales, const float *means, const float *noise,
+                          int likelihood_only, int64_t n, float scale_bound, float lik_bound,
+                          float *g_inputs, float *g_scales, float *g_means, pic_stream_t stream);
+int pic_build_indexes(const float *scales, int64_t n, const float *scale_table, int table_len,
+                      float scale_bound, int32_t *idx, pic_stream_t stream);
+int pic_quantize(const float *inputs, const float *means, const float *noise, const float *mask,
+                 int64_t n, int mode, float *out_f32, int32_t *out_i32, pic_stream_t stream);
+int pic_dequantize(const int32_t *symbols, const float *means, int64_t n, float *out,
+                   pic_stream_t stream);
+int pic_log_sum(const float *x, int64_t n_per_unit, int64_t units, double *out,
+                pic_stream_t stream);
+
+/*
+ * (6) Host-buffer form of (3) for callers whose latents live in host memory (the reference's
+ * CPU path, or an FFI caller without device tensors).  All tensor pointers are HOST memory
+ * (pinned memory makes the copies asynchronous); units are streamed through the device in
+ * chunks with the copies overlapping the kernel.  Blocks until the outputs are in host memory.
+ * `device_buf`/`device_buf_bytes`: caller-owned device scratch of at least
+ * pic_host_pipeline_bytes(n_per_unit, chunk_units) bytes.
+ */
+size_t pic_host_pipeline_bytes(int64_t n_per_unit, int64_t chunk_units);
+int pic_slice_forward_host(const float *y_top, const float *y_base, const float *mu,
+                           const float *std, float q01, const float *q01_per_unit_host,
+                           const float *noise, const float *scale_table_host, int table_len,
+                           float scale_bound, float lik_bound, int64_t n_per_unit, int64_t units,
+                           int64_t chunk_units, float *mask, float *y_hat, float *lik,
+                           int32_t *idx, int32_t *symbols, float *thr_out, double *rate,
+                           void *device_buf, size_t device_buf_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC_LATENT_H_ */

@@ -1,0 +1,133 @@
+"""CPU: C-ABI surface, host-side logic of the drop-in classes, error behaviour.  No kernels run."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pic_b200
+from pic_b200 import _lib, ops
+from pic_b200.distributed import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    pic_b200.build()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pic_latent.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pic_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 24
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/pic_latent.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "python binding table out of sync with the header"
+
+
+def test_library_loads_without_gpu():
+    L = pic_b200.lib()
+    assert L.pic_version() >= 100
+    assert L.pic_fused_max_elems() >= 49152  # a Kodak-shape unit must take the fused path
+    assert L.pic_hist_words() >= 2049
+    assert L.pic_error_string(-2) == b"quantile() input tensor is too large"
+    assert L.pic_workspace_bytes(8192, 10) > 0
+    assert L.pic_workspace_bytes(1 << 23, 10) >= 10 * 3 * 2048 * 4
+    assert L.pic_host_pipeline_bytes(8192, 4) >= 3 * 10 * 4 * 8192 * 4
+
+
+def test_sm100a_sass_only():
+    """The shared object carries sm_100a code (and nothing older)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_pr_to_q01_matches_reference_arithmetic():
+    assert ops.pr_to_q01(10) == _lib.Q_ONES and ops.pr_to_q01(11.5) == _lib.Q_ONES
+    assert ops.pr_to_q01(0) == _lib.Q_ZEROS
+    for pr in (1e-4, 0.5, 0.75, 1, 2.5, 5, 7.3, 9.9999):
+        p = pr * 0.1
+        assert ops.pr_to_q01(pr) == 1.0 - p  # channel_mask.py:138-140, double arithmetic
+        assert 0.0 <= ops.pr_to_q01(pr) <= 1.0
+
+
+def test_shard_range_partitions():
+    for total, world in ((256, 8), (10, 4), (3, 8), (1010, 8)):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_channel_mask_shortcuts_and_errors_on_cpu():
+    m = pic_b200.ChannelMask("point-based-std")
+    s = torch.randn(2, 32, 4, 4)
+    assert torch.equal(m(s, pr=10), torch.ones_like(s)) and torch.equal(m(s, pr=0), torch.zeros_like(s))
+    assert torch.equal(m(s, pr=0, mask_pol="two-levels"), torch.zeros_like(s))
+    assert torch.equal(m(s, pr=2, mask_pol="two-levels"), torch.ones_like(s))
+    with pytest.raises(NotImplementedError):
+        m(s, pr=2, mask_pol="unknown-policy")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):  # no CPU fallback on the product path
+        m(s, pr=5)
+    with pytest.raises(ValueError):  # wrong rank, like the reference's tuple unpack
+        m(torch.randn(4, 4), pr=5)
+
+
+def test_gaussian_conditional_constructor_and_buffers():
+    table = pic_b200.get_scale_table()
+    assert table.shape == (64,) and abs(float(table[0]) - 0.11) < 1e-7 and abs(float(table[-1]) - 256) < 1e-3
+    gc = pic_b200.GaussianConditional(None)
+    keys = set(gc.state_dict().keys())
+    assert keys == {"_offset", "_quantized_cdf", "_cdf_length", "scale_table", "scale_bound",
+                    "likelihood_lower_bound.bound", "lower_bound_scale.bound"}
+    assert gc._bounds() == (float(np.float32(0.11)), float(np.float32(1e-9)))
+    gc2 = pic_b200.GaussianConditional([0.2, 0.5, 1.0], scale_bound=0.2, likelihood_bound=0)
+    assert gc2.scale_table.tolist() == [float(np.float32(v)) for v in (0.2, 0.5, 1.0)]
+    assert not gc2.use_likelihood_bound and gc2._bounds()[1] == 0.0
+    for bad in ("x", [], [1.0, 0.5], [0.0, 1.0]):
+        with pytest.raises(ValueError):
+            pic_b200.GaussianConditional(bad)
+    with pytest.raises(ValueError):
+        pic_b200.GaussianConditional(None, scale_bound=0)
+    with pytest.raises(ValueError, match="Invalid quantization mode"):
+        gc.quantize(torch.zeros(4), "bogus")
+    # a state_dict with a different bound re-arms the cached scalar
+    sd = gc.state_dict()
+    sd["lower_bound_scale.bound"] = torch.tensor([0.25])
+    gc.load_state_dict(sd)
+    assert gc._bounds()[0] == 0.25
+
+
+def test_lower_bound_autograd_matches_compressai_rule():
+    lb = pic_b200.LowerBound(0.5)
+    x = torch.tensor([0.2, 0.5, 0.9, 0.1], requires_grad=True)
+    y = lb(x)
+    assert y.tolist() == [0.5, 0.5, 0.8999999761581421, 0.5]
+    y.backward(torch.tensor([1.0, 1.0, 1.0, -1.0]))
+    assert x.grad.tolist() == [0.0, 1.0, 1.0, -1.0]
+
+
+def test_ops_reject_bad_inputs_without_touching_the_gpu():
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.build_indexes(torch.zeros(8), torch.ones(64))
+    with pytest.raises(ValueError, match="Invalid quantization mode"):
+        ops.quantize(torch.zeros(8), "nope")
+    with pytest.raises(TypeError):
+        ops._require(np.zeros(3), "x")
