@@ -22,6 +22,7 @@
 
 #include "../../include/pic_latent.h"
 #include "pic_math.cuh"
+#include "pic_fast.cuh"
 #include "pic_select.cuh"
 
 namespace pic {
@@ -94,33 +95,50 @@ struct SelectState {
 static_assert(sizeof(SelectState) == 64, "SelectState must stay 64 bytes");
 
 // ------------------------------------------------------------------------------------------
-// per-element apply
+// per-element apply (two elements per call: pic_fast.cuh::apply_pair)
 // ------------------------------------------------------------------------------------------
-struct ElemOut {
-    float m, y_hat, lik;
-    int32_t idx, sym;
-};
+// Shared-memory staging of the scale table for the index computation.  Layout (floats):
+// [0,64) table copy, [64,192) float2 pairs (tbl[k-1], tbl[k]), [192] lg2(t0), [193] inv_step,
+// [194] geometric flag.
+constexpr int kIndexSmemFloats = 64 + 128 + 8;
 
-template <bool TRAIN>
-__device__ __forceinline__ ElemOut apply_one(const SliceParams &p, float s, float yt, float yb,
-                                             float mu, float nz, int mode, float thr,
-                                             const float *tbl, bool tbl64) {
-    ElemOut o;
-    const float m = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s >= thr) ? 1.0f : 0.0f);
-    const float r = p.y_base ? __fsub_rn(yt, yb) : yt;       // pic.py:583-584
-    const float d = __fsub_rn(r, mu);                         // pic.py:625
-    const float y_m = __fmul_rn(d, m);                        // pic.py:626
-    const float s_m = __fmul_rn(s, m);                        // pic.py:628 (scale*block_mask)
-    const float out = TRAIN ? __fadd_rn(y_m, nz) : rintf(y_m);  // quantize("noise"|"dequantize")
-    o.m = m;
-    o.lik = (p.lik || p.rate) ? likelihood(out, s_m, p.scale_bound, p.lik_bound) : 0.0f;
-    const float rd = rintf(d);
-    const float ste = __fadd_rn(__fsub_rn(rd, d), d);         // ste_round forward value
-    o.y_hat = __fadd_rn(__fmul_rn(ste, m), mu);               // pic.py:629
-    o.idx = 0;
-    if (p.idx) o.idx = tbl64 ? scale_index64(s_m, p.scale_bound, tbl) : scale_index(s_m, p.scale_bound, tbl, p.table_len);
-    o.sym = __float2int_rn(y_m);                              // quantize(.., "symbols")
-    return o;
+__device__ __forceinline__ IndexCtx index_ctx_setup(const SliceParams &p, float *sm) {
+    IndexCtx ic;
+    ic.len = p.table_len;
+    ic.tbl64 = (p.table_len == kTableSmem) && p.idx;
+    ic.tbl = p.table;
+    ic.pairs = nullptr;
+    ic.geometric = false;
+    ic.lg2_t0 = 0.0f;
+    ic.inv_step = 0.0f;
+    if (!ic.tbl64) return ic;  // uniform
+    const int tid = threadIdx.x;
+    float2 *pairs = reinterpret_cast<float2 *>(sm + 64);
+    if (tid < kTableSmem) {
+        const float t = p.table[tid];
+        sm[tid] = t;
+        const float prev = (tid == 0) ? -INFINITY : p.table[tid - 1];
+        pairs[tid] = make_float2(prev, (tid == kTableSmem - 1) ? INFINITY : t);
+    }
+    if (tid == 0) {
+        const float l0 = lg2_approx(p.table[0]);
+        const float l1 = lg2_approx(p.table[kTableSmem - 1]);
+        sm[192] = l0;
+        sm[193] = static_cast<float>(kTableSmem - 1) / (l1 - l0);
+    }
+    __syncthreads();
+    bool ok = true;
+    if (tid < kTableSmem) {
+        const float x = (lg2_approx(sm[tid]) - sm[192]) * sm[193];
+        ok = fabsf(x - static_cast<float>(tid)) < 0.25f;      // guess lands within +-1 of the answer
+    }
+    const int all_ok = __syncthreads_and(ok ? 1 : 0);
+    ic.tbl = sm;
+    ic.pairs = pairs;
+    ic.lg2_t0 = sm[192];
+    ic.inv_step = sm[193];
+    ic.geometric = all_ok != 0 && (sm[193] > 0.0f);
+    return ic;
 }
 
 // Applies the slice arithmetic to elements [0, len) of a unit-local range starting at global
@@ -128,16 +146,21 @@ __device__ __forceinline__ ElemOut apply_one(const SliceParams &p, float s, floa
 // first element of the range); otherwise from global memory.
 template <bool TRAIN, bool VEC, int THREADS>
 __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, int len,
-                                             const uint32_t *keys, int mode, float thr,
-                                             const float *tbl, bool tbl64) {
+                                             const uint32_t *keys, int mode, float thr_in,
+                                             const IndexCtx &ic) {
     float rate_acc = 0.0f;
     const int tid = threadIdx.x;
     const bool full = p.apply_kind == 2;
+    const bool force_one = mode == kModeOnes;
+    const float thr = (mode == kModeZeros) ? __int_as_float(0x7fc00000) : thr_in;  // s >= NaN is false
+    const bool has_base = p.y_base != nullptr;
+    const bool want_lik = (p.lik != nullptr) || (p.rate != nullptr);
+    const bool want_idx = p.idx != nullptr, want_sym = p.symbols != nullptr;
     if (VEC) {
         const int nvec = len >> 2;
         const float4 *std4 = reinterpret_cast<const float4 *>(p.std + off);
         const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top + off);
-        const float4 *yb4 = p.y_base ? reinterpret_cast<const float4 *>(p.y_base + off) : nullptr;
+        const float4 *yb4 = has_base ? reinterpret_cast<const float4 *>(p.y_base + off) : nullptr;
         const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu + off);
         const float4 *nz4 = TRAIN ? reinterpret_cast<const float4 *>(p.noise + off) : nullptr;
         const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
@@ -154,48 +177,51 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
             if (!full) {
                 float mk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    mk[e] = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s[e] >= thr) ? 1.0f : 0.0f);
+                for (int e = 0; e < 4; ++e) mk[e] = ((s[e] >= thr) || force_one) ? 1.0f : 0.0f;
                 reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(mk[0], mk[1], mk[2], mk[3]);
                 continue;
             }
             const float4 ytv = __ldg(yt4 + j);
             const float4 muv = __ldg(mu4 + j);
             float4 ybv = make_float4(0.f, 0.f, 0.f, 0.f), nzv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yb4) ybv = __ldg(yb4 + j);
+            if (has_base) ybv = __ldg(yb4 + j);
             if (TRAIN) nzv = __ldg(nz4 + j);
             const float yt[4] = {ytv.x, ytv.y, ytv.z, ytv.w}, yb[4] = {ybv.x, ybv.y, ybv.z, ybv.w};
             const float mu[4] = {muv.x, muv.y, muv.z, muv.w}, nz[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
-            ElemOut o[4];
+            PairOut o[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                o[e] = apply_one<TRAIN>(p, s[e], yt[e], yb[e], mu[e], nz[e], mode, thr, tbl, tbl64);
-                if (p.rate) rate_acc += logf(o[e].lik);
+            for (int h = 0; h < 2; ++h) {
+                apply_pair<TRAIN>(s + 2 * h, yt + 2 * h, yb + 2 * h, mu + 2 * h, nz + 2 * h, has_base, thr,
+                                  force_one, p.scale_bound, p.lik_bound, want_lik, want_idx, want_sym, ic, o[h]);
+                if (p.rate) rate_acc += logf(o[h].lik[0]) + logf(o[h].lik[1]);
             }
-            if (p.mask) reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(o[0].m, o[1].m, o[2].m, o[3].m);
-            if (p.y_hat) reinterpret_cast<float4 *>(p.y_hat + off)[j] = make_float4(o[0].y_hat, o[1].y_hat, o[2].y_hat, o[3].y_hat);
-            if (p.lik) reinterpret_cast<float4 *>(p.lik + off)[j] = make_float4(o[0].lik, o[1].lik, o[2].lik, o[3].lik);
-            if (p.idx) reinterpret_cast<int4 *>(p.idx + off)[j] = make_int4(o[0].idx, o[1].idx, o[2].idx, o[3].idx);
-            if (p.symbols) reinterpret_cast<int4 *>(p.symbols + off)[j] = make_int4(o[0].sym, o[1].sym, o[2].sym, o[3].sym);
+            if (p.mask) reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(o[0].m[0], o[0].m[1], o[1].m[0], o[1].m[1]);
+            if (p.y_hat) reinterpret_cast<float4 *>(p.y_hat + off)[j] = make_float4(o[0].y_hat[0], o[0].y_hat[1], o[1].y_hat[0], o[1].y_hat[1]);
+            if (p.lik) reinterpret_cast<float4 *>(p.lik + off)[j] = make_float4(o[0].lik[0], o[0].lik[1], o[1].lik[0], o[1].lik[1]);
+            if (want_idx) reinterpret_cast<int4 *>(p.idx + off)[j] = make_int4(o[0].idx[0], o[0].idx[1], o[1].idx[0], o[1].idx[1]);
+            if (want_sym) reinterpret_cast<int4 *>(p.symbols + off)[j] = make_int4(o[0].sym[0], o[0].sym[1], o[1].sym[0], o[1].sym[1]);
         }
     } else {
         for (int j = tid; j < len; j += THREADS) {
-            const float s = keys ? key_to_float(keys[j]) : __ldg(p.std + off + j);
+            const float sv = keys ? key_to_float(keys[j]) : __ldg(p.std + off + j);
             if (!full) {
-                p.mask[off + j] = (mode == kModeOnes) ? 1.0f : (mode == kModeZeros) ? 0.0f : ((s >= thr) ? 1.0f : 0.0f);
+                p.mask[off + j] = ((sv >= thr) || force_one) ? 1.0f : 0.0f;
                 continue;
             }
-            const float yt = __ldg(p.y_top + off + j);
-            const float yb = p.y_base ? __ldg(p.y_base + off + j) : 0.0f;
-            const float mu = __ldg(p.mu + off + j);
-            const float nz = TRAIN ? __ldg(p.noise + off + j) : 0.0f;
-            const ElemOut o = apply_one<TRAIN>(p, s, yt, yb, mu, nz, mode, thr, tbl, tbl64);
-            if (p.rate) rate_acc += logf(o.lik);
-            if (p.mask) p.mask[off + j] = o.m;
-            if (p.y_hat) p.y_hat[off + j] = o.y_hat;
-            if (p.lik) p.lik[off + j] = o.lik;
-            if (p.idx) p.idx[off + j] = o.idx;
-            if (p.symbols) p.symbols[off + j] = o.sym;
+            const float ytv = __ldg(p.y_top + off + j);
+            const float ybv = has_base ? __ldg(p.y_base + off + j) : 0.0f;
+            const float muv = __ldg(p.mu + off + j);
+            const float nzv = TRAIN ? __ldg(p.noise + off + j) : 0.0f;
+            const float s[2] = {sv, sv}, yt[2] = {ytv, ytv}, yb[2] = {ybv, ybv}, mu[2] = {muv, muv}, nz[2] = {nzv, nzv};
+            PairOut o;
+            apply_pair<TRAIN>(s, yt, yb, mu, nz, has_base, thr, force_one, p.scale_bound, p.lik_bound, want_lik,
+                              want_idx, want_sym, ic, o);
+            if (p.rate) rate_acc += logf(o.lik[0]);
+            if (p.mask) p.mask[off + j] = o.m[0];
+            if (p.y_hat) p.y_hat[off + j] = o.y_hat[0];
+            if (p.lik) p.lik[off + j] = o.lik[0];
+            if (want_idx) p.idx[off + j] = o.idx[0];
+            if (want_sym) p.symbols[off + j] = o.sym[0];
         }
     }
     return rate_acc;
@@ -229,11 +255,9 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
     uint32_t *hist = keys + n_pad;
     uint32_t *scratch = hist + kHistBins;
     float *tbl = reinterpret_cast<float *>(scratch + kScratchWords);
-    double *red = reinterpret_cast<double *>(tbl + kTableSmem);
+    double *red = reinterpret_cast<double *>(tbl + kIndexSmemFloats);
     const int tid = threadIdx.x;
-    const bool tbl64 = (p.table_len == kTableSmem) && p.idx;
-    if (tbl64 && tid < kTableSmem) tbl[tid] = p.table[tid];
-    const float *tbl_ptr = tbl64 ? tbl : p.table;
+    const IndexCtx ic = index_ctx_setup(p, tbl);
 
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int64_t off = u * p.n;
@@ -299,7 +323,7 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
             if (p.b_out) p.b_out[u] = b_val;
         }
         if (p.apply_kind != 0) {
-            const float acc = apply_range<TRAIN, VEC, THREADS>(p, off, n, staged ? keys : nullptr, mode, thr, tbl_ptr, tbl64);
+            const float acc = apply_range<TRAIN, VEC, THREADS>(p, off, n, staged ? keys : nullptr, mode, thr, ic);
             if (p.rate) {
                 const double total = block_sum_f64<THREADS>(acc, red);
                 if (tid == 0) p.rate[u] = total;
@@ -460,12 +484,10 @@ __global__ void select_finish_kernel(const SelectState *state, const uint32_t *m
 template <bool TRAIN, bool VEC>
 __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, int tiles_per_unit) {
     constexpr int THREADS = 256;
-    __shared__ float tbl[kTableSmem];
+    __shared__ __align__(16) float tbl[kIndexSmemFloats];
     __shared__ double red[THREADS / 32];
     const int tid = threadIdx.x;
-    const bool tbl64 = (p.table_len == kTableSmem) && p.idx;
-    if (tbl64 && tid < kTableSmem) tbl[tid] = p.table[tid];
-    if (tbl64) __syncthreads();
+    const IndexCtx ic = index_ctx_setup(p, tbl);
     const int64_t u = blockIdx.x / tiles_per_unit;
     const int tile = blockIdx.x - static_cast<int>(u) * tiles_per_unit;
     const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
@@ -474,8 +496,7 @@ __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, i
     if (tile == 0 && tid == 0 && p.thr_out) p.thr_out[u] = thr;
     const int64_t begin = static_cast<int64_t>(tile) * kApplyTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kApplyTile), p.n - begin));
-    const float acc = apply_range<TRAIN, VEC, THREADS>(p, u * p.n + begin, len, nullptr, mode, thr,
-                                                      tbl64 ? tbl : p.table, tbl64);
+    const float acc = apply_range<TRAIN, VEC, THREADS>(p, u * p.n + begin, len, nullptr, mode, thr, ic);
     if (p.rate) {
         const double total = block_sum_f64<THREADS>(acc, red);
         if (tid == 0) atomicAdd(&p.rate[u], total);
@@ -704,7 +725,7 @@ __global__ void __launch_bounds__(256) log_sum_kernel(const float *x, int64_t n_
 // ------------------------------------------------------------------------------------------
 static size_t fused_smem_bytes(int64_t n) {
     const int64_t n_pad = (n + 3) & ~int64_t(3);
-    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kScratchWords * 4 + kTableSmem * 4 + 32 * 8;
+    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kScratchWords * 4 + kIndexSmemFloats * 4 + 32 * 8;
 }
 
 template <bool TRAIN, bool VEC, int THREADS>
