@@ -248,13 +248,19 @@ def run_cuda(args, wl):
 
     launches_per_step = [0]
 
+    q_all = torch.cat([q_slice] * slices).contiguous()
+
     def step():
         cnt = 0
-        for s in range(slices):
-            o = {k: view(v, s) for k, v in outs.items()}
-            ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice, table,
-                              want=want, out=o)
-            cnt += 1 if fused else 9  # rounds path: begin + 3x(hist, advance) + finish + apply
+        if args.launch == "per_step":
+            ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
+            cnt = 1 if fused else 9
+        else:
+            for s in range(slices):
+                o = {k: view(v, s) for k, v in outs.items()}
+                ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice,
+                                  table, want=want, out=o)
+                cnt += 1 if fused else 9  # rounds path: begin + 3x(hist, advance) + finish + apply
         launches_per_step[0] = cnt
 
     def barrier():
@@ -340,8 +346,9 @@ def run_cuda(args, wl):
 
     hbm, which = peaks()
     launches = launches_per_step[0] * args.steps
-    kern_ms = ms_per_step / slices  # fused path: one kernel per slice launch, back to back
-    bytes_per_launch = per_slice * n * BYTES_PER_ELEM
+    n_launch = 1 if args.launch == "per_step" else slices
+    kern_ms = ms_per_step / n_launch  # fused path: the step is n_launch back-to-back launches of one kernel
+    bytes_per_launch = units // n_launch * n * BYTES_PER_ELEM
     achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -358,7 +365,7 @@ def run_cuda(args, wl):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
-                   "units_per_launch": per_slice, "units_per_step_per_gpu": units, "launches_per_step": launches_per_step[0],
+                   "units_per_launch": units if args.launch == "per_step" else per_slice, "launch": args.launch, "units_per_step_per_gpu": units, "launches_per_step": launches_per_step[0],
                    "outputs": list(want), "bytes_per_elem": BYTES_PER_ELEM,
                    "l2": f"inputs of one step = {units * n * 16 / 1e6:.0f} MB > 126 MB L2, no explicit flush",
                    "parallelism": f"units sharded, {world} rank(s), no collective"},
@@ -379,6 +386,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS))
+    ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
+                    help="per_step: all (slice, q) units of a step in one launch; per_slice: one launch per slice index")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

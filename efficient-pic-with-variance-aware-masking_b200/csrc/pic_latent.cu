@@ -65,8 +65,8 @@ static int sm_count() {
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
-constexpr int kFusedMaxElems = 55296;   // 216 KiB of keys + 8 KiB histogram + scratch <= 227 KiB
-constexpr int kScratchWords = 64;
+constexpr int kFusedMaxElems = 51200;   // 200 KiB keys + 8 KiB histogram + 16 KiB candidates + scratch <= 227 KiB
+constexpr int kScratchWords = 64;  // block_select uses [0,48)
 constexpr int kTableSmem = 64;
 constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
 constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
     const int n_pad = (n + 3) & ~3;
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *hist = keys + n_pad;
-    uint32_t *scratch = hist + kHistBins;
+    uint32_t *cand = hist + kHistBins;
+    uint32_t *scratch = cand + kCandMax;
     float *tbl = reinterpret_cast<float *>(scratch + kScratchWords);
     double *red = reinterpret_cast<double *>(tbl + kIndexSmemFloats);
     const int tid = threadIdx.x;
@@ -283,25 +284,31 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
                     const bool inb = j < nvec;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (inb) v = __ldg(std4 + j);
-                    const float s[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t k[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        has_nan |= (s[e] != s[e]);
-                        k[e] = float_to_key(s[e]);
-                        hist_add(hist, k[e] >> round_shift(0), inb);
+                    has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+                    const uint32_t k0 = float_to_key(v.x), k1 = float_to_key(v.y);
+                    const uint32_t k2 = float_to_key(v.z), k3 = float_to_key(v.w);
+                    const uint32_t d0 = k0 >> 21, d1 = k1 >> 21, d2 = k2 >> 21, d3 = k3 >> 21;
+                    // flat regions (128 consecutive values in one bin) are common in real std maps:
+                    // one atomic for the warp instead of 128 same-address ones
+                    const uint32_t lead = __shfl_sync(0xffffffffu, d0, 0);
+                    const bool run = __all_sync(0xffffffffu, inb && ((d0 ^ lead) | (d1 ^ lead) | (d2 ^ lead) | (d3 ^ lead)) == 0u);
+                    if (run) {
+                        if ((tid & 31) == 0) atomicAdd(&hist[lead], 128u);
+                    } else if (inb) {
+                        atomicAdd(&hist[d0], 1u);
+                        atomicAdd(&hist[d1], 1u);
+                        atomicAdd(&hist[d2], 1u);
+                        atomicAdd(&hist[d3], 1u);
                     }
-                    if (inb) reinterpret_cast<uint4 *>(keys)[j] = make_uint4(k[0], k[1], k[2], k[3]);
+                    if (inb) reinterpret_cast<uint4 *>(keys)[j] = make_uint4(k0, k1, k2, k3);
                 }
             } else {
-                for (int jb = tid - (tid & 31); jb < n; jb += THREADS) {
-                    const int j = jb + (tid & 31);
-                    const bool inb = j < n;
-                    const float s = inb ? __ldg(p.std + off + j) : 0.0f;
-                    has_nan |= (s != s);
-                    const uint32_t k = float_to_key(s);
-                    hist_add(hist, k >> round_shift(0), inb);
-                    if (inb) keys[j] = k;
+                for (int j = tid; j < n; j += THREADS) {
+                    const float sv = __ldg(p.std + off + j);
+                    has_nan |= (sv != sv);
+                    const uint32_t k = float_to_key(sv);
+                    atomicAdd(&hist[k >> 21], 1u);
+                    keys[j] = k;
                 }
             }
             if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
             float w;
             quantile_ranks(q, p.n, lo, hi, w);
             uint32_t a_key, b_key;
-            block_select<THREADS>(keys, n, hist, scratch, lo, hi, true, a_key, b_key);
+            block_select<THREADS>(keys, n, hist, cand, scratch, lo, hi, true, a_key, b_key);
             a_val = key_to_float(a_key);
             b_val = key_to_float(b_key);
             thr = quantile_lerp(a_val, b_val, w);
@@ -725,7 +732,7 @@ __global__ void __launch_bounds__(256) log_sum_kernel(const float *x, int64_t n_
 // ------------------------------------------------------------------------------------------
 static size_t fused_smem_bytes(int64_t n) {
     const int64_t n_pad = (n + 3) & ~int64_t(3);
-    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kScratchWords * 4 + kIndexSmemFloats * 4 + 32 * 8;
+    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kCandMax * 4 + kScratchWords * 4 + kIndexSmemFloats * 4 + 32 * 8;
 }
 
 template <bool TRAIN, bool VEC, int THREADS>

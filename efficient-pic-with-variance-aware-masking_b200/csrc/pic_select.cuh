@@ -116,18 +116,51 @@ __device__ __forceinline__ uint32_t block_next_nonempty(const uint32_t *hist, in
     return r;
 }
 
-// One CTA selects keys[lo] and keys[hi] (ascending order statistics) among n keys held in
-// shared memory.  hist: kHistBins words; scratch: 40 words.  If round0_ready the caller has
-// already accumulated the round-0 histogram while staging the keys.
+constexpr int kCandMax = 4096;  // candidate buffer (keys of the chosen round-0/1 bucket)
+
+// Histogram of digit `r` over keys[0..n) restricted to keys whose higher bits equal those of
+// `prefix`.  Plain shared-memory atomics: after round 0 the matching keys are a small subset
+// (or the whole, already small, candidate buffer).
+template <int THREADS>
+__device__ __forceinline__ void block_hist_pass(const uint32_t *keys, int n, uint32_t *hist, int r,
+                                                uint32_t prefix) {
+    const int shift = round_shift(r);
+    const int up = (r == 0) ? 32 : shift + (r == 1 ? 11 : 10);
+    const uint32_t want = (r == 0) ? 0u : (prefix >> up);
+    const uint32_t mask = round_mask(r);
+    const int tid = threadIdx.x;
+    const int nvec = n >> 2;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+    for (int j = tid; j < nvec; j += THREADS) {
+        const uint4 k = k4[j];
+        const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (r == 0 || (kk[e] >> up) == want) atomicAdd(&hist[(kk[e] >> shift) & mask], 1u);
+    }
+    for (int j = (nvec << 2) + tid; j < n; j += THREADS) {
+        const uint32_t k = keys[j];
+        if (r == 0 || (k >> up) == want) atomicAdd(&hist[(k >> shift) & mask], 1u);
+    }
+}
+
+// One CTA selects the order statistics lo and hi (hi in {lo, lo+1}) among n keys held in
+// shared memory.  hist: kHistBins words; cand: kCandMax words; scratch: 48 words.
+// round0_ready: the caller accumulated the round-0 histogram while staging the keys.
+// After any round whose chosen bin holds <= kCandMax keys the bin is compacted into `cand`
+// and the remaining rounds (and the successor search) run on the candidates only.
 template <int THREADS>
 __device__ __forceinline__ void block_select(const uint32_t *keys, int n, uint32_t *hist,
-                                             uint32_t *scratch, uint32_t lo, uint32_t hi,
-                                             bool round0_ready, uint32_t &a_key, uint32_t &b_key) {
+                                             uint32_t *cand, uint32_t *scratch, uint32_t lo,
+                                             uint32_t hi, bool round0_ready, uint32_t &a_key,
+                                             uint32_t &b_key) {
     const int tid = threadIdx.x;
     uint32_t prefix = 0;        // key bits decided so far (in place)
     uint32_t rank = lo;         // rank of `a` among keys matching the prefix
     uint32_t below_total = 0;   // keys strictly below the current prefix bucket
-    uint32_t min_above = 0xffffffffu;  // smallest key above the final 22-bit bucket
+    const uint32_t *cur = keys;
+    int cur_n = n;
+    bool compacted = false;
     BinHit hit{0, 0, 0};
 #pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
@@ -136,65 +169,61 @@ __device__ __forceinline__ void block_select(const uint32_t *keys, int n, uint32
         if (!(r == 0 && round0_ready)) {
             for (int j = tid; j < nbins; j += THREADS) hist[j] = 0u;
             __syncthreads();
-            const int nvec = n >> 2;
-            const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
-            for (int jb = tid - (tid & 31); jb < nvec; jb += THREADS) {  // warp-uniform trip count
-                const int j = jb + (tid & 31);
-                const bool inb = j < nvec;
-                uint4 k = inb ? k4[j] : make_uint4(0, 0, 0, 0);
-                const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    bool match = inb;
-                    if (r > 0) {
-                        const uint32_t hi_bits = kk[e] >> (shift + (r == 1 ? 11 : 10));
-                        const uint32_t want = prefix >> (shift + (r == 1 ? 11 : 10));
-                        if (r == 2 && inb && hi_bits > want) min_above = min(min_above, kk[e]);
-                        match = inb && (hi_bits == want);
-                    }
-                    hist_add(hist, (kk[e] >> shift) & round_mask(r), match);
-                }
-            }
-            // scalar tail (n % 4)
-            {
-                const int j = (nvec << 2) + tid;
-                const bool inb = (tid < 32) && (j < n);
-                if (tid < 32) {
-                    const uint32_t k = inb ? keys[j] : 0u;
-                    bool match = inb;
-                    if (r > 0) {
-                        const uint32_t hi_bits = k >> (shift + (r == 1 ? 11 : 10));
-                        const uint32_t want = prefix >> (shift + (r == 1 ? 11 : 10));
-                        if (r == 2 && inb && hi_bits > want) min_above = min(min_above, k);
-                        match = inb && (hi_bits == want);
-                    }
-                    hist_add(hist, (k >> shift) & round_mask(r), match);
-                }
-            }
+            block_hist_pass<THREADS>(cur, cur_n, hist, r, prefix);
             __syncthreads();
         }
         hit = block_find_bin<THREADS>(hist, nbins, rank, scratch);
         prefix |= hit.bin << shift;
         rank -= hit.below;
         below_total += hit.below;
+        if (r < 2 && !compacted && hit.count <= static_cast<uint32_t>(kCandMax)) {
+            // compact the chosen bucket: keys whose top (32 - shift) bits equal the prefix's
+            if (tid == 0) scratch[40] = 0u;
+            __syncthreads();
+            const uint32_t want = prefix >> shift;
+            const int nvec = n >> 2;
+            const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+            for (int j = tid; j < nvec; j += THREADS) {
+                const uint4 k = k4[j];
+                const uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((kk[e] >> shift) == want) cand[atomicAdd(&scratch[40], 1u)] = kk[e];
+            }
+            for (int j = (nvec << 2) + tid; j < n; j += THREADS) {
+                const uint32_t k = keys[j];
+                if ((k >> shift) == want) cand[atomicAdd(&scratch[40], 1u)] = k;
+            }
+            __syncthreads();
+            cur = cand;
+            cur_n = static_cast<int>(hit.count);
+            compacted = true;
+        }
     }
     a_key = prefix;
-    // multiplicity of a is hit.count; ranks [below_total, below_total + count) all hold a.
+    // ranks [below_total, below_total + hit.count) all hold a
     if (hi < below_total + hit.count) {
         b_key = a_key;
-    } else {
-        const uint32_t nb = block_next_nonempty<THREADS>(hist, round_bins(2), hit.bin, scratch);
-        if (nb != 0xffffffffu) {
-            b_key = (prefix & ~round_mask(2)) | nb;
-        } else {
-            min_above = __reduce_min_sync(0xffffffffu, min_above);
-            if (tid == 0) scratch[38] = 0xffffffffu;
-            __syncthreads();
-            if ((tid & 31) == 0) atomicMin(&scratch[38], min_above);
-            __syncthreads();
-            b_key = scratch[38];
-            __syncthreads();
+        return;
+    }
+    // successor of a: smallest key > a.  It lies in the candidate bucket unless a is its maximum.
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid == 0) scratch[38] = 0xffffffffu;
+        __syncthreads();
+        uint32_t best = 0xffffffffu;
+        for (int j = tid; j < cur_n; j += THREADS) {
+            const uint32_t k = cur[j];
+            if (k > a_key) best = min(best, k);
         }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&scratch[38], best);
+        __syncthreads();
+        b_key = scratch[38];
+        __syncthreads();
+        if (b_key != 0xffffffffu || !compacted) break;
+        cur = keys;   // a was the bucket maximum: look at the whole unit (rare)
+        cur_n = n;
+        compacted = false;
     }
 }
 

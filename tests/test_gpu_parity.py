@@ -203,7 +203,7 @@ def test_channel_mask_api_errors(pic, dev):
 
 
 # ------------------------------------------------------------------ seeded comparisons with the oracle
-ORACLE_SHAPES = [(1, 4), (3, 32), (2, 1001), (5, 1120), (4, 8192), (3, 49152), (2, 55296), (2, 55300),
+ORACLE_SHAPES = [(1, 4), (3, 32), (2, 1001), (5, 1120), (4, 8192), (3, 49152), (2, 51200), (2, 51204), (2, 55300),
                  (2, 200000), (1, 1 << 20), (3, 65537)]
 
 
