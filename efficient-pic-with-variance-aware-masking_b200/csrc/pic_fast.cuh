@@ -73,6 +73,42 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// L2 eviction-priority hints: the unit's std is read twice (select sweep, then apply) and should
+// stay in L2 in between; everything else is touched exactly once and is streamed.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_hint(const float4 *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(float4 *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(int4 *p, int4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS) with an L2 policy; per-thread private slots
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, uint64_t pol) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // NaN-propagating min / max (torch.max(x, bound) semantics of LowerBound)
 __device__ __forceinline__ float max_nan(float a, float b) {
     float r;
@@ -131,23 +167,22 @@ struct PairOut {
 
 struct IndexCtx {
     const float *tbl;     // table (shared memory copy when table_len == 64)
-    const float2 *pairs;  // pairs[k] = (tbl[k-1], tbl[k]) for the fix-up (shared memory), or nullptr
-    float lg2_t0;         // log2(tbl[0])
     float inv_step;       // (len-1) / (log2(tbl[len-1]) - log2(tbl[0]))
+    float bias;           // -(log2(tbl[0]) * inv_step + eps)
     int len;
     bool geometric;       // guess-and-fix is valid
     bool tbl64;
 };
 
-// idx = #{j < len-1 : tbl[j] < sc}  (== build_indexes on a sorted table)
+// idx = #{j < len-1 : tbl[j] < sc}  (== build_indexes on a sorted table).
+// Geometric table: g = floor(x - eps) + 1 with x = (lg2 sc - lg2 t0) * inv_step is idx or idx-1
+// (|error of x| << eps << 1), so one comparison against the real table entry makes it exact.
+// fminf() maps NaN / huge sc to the last index (non-propagating min returns the other operand).
 __device__ __forceinline__ int scale_index_fast(float sc, const IndexCtx &c) {
     if (!c.geometric) return c.tbl64 ? scale_index64(sc, 0.0f, c.tbl) : scale_index(sc, 0.0f, c.tbl, c.len);
-    const float x = __fmaf_rn(lg2_approx(sc), c.inv_step, -c.lg2_t0 * c.inv_step);
-    int k = __float2int_rd(x) + 1;                 // NaN -> 0 + 1
-    k = max(0, min(k, c.len - 1));
-    const float2 tb = c.pairs[k];                  // (tbl[k-1] or -inf, tbl[k] or +inf at len-1)
-    k = (sc <= tb.x) ? k - 1 : ((tb.y < sc) ? k + 1 : k);
-    return (sc != sc) ? c.len - 1 : k;
+    const float x = fminf(__fmaf_rn(lg2_approx(sc), c.inv_step, c.bias), static_cast<float>(c.len) - 1.5f);
+    const int g = max(__float2int_rd(x) + 1, 0);
+    return (g < c.len - 1 && c.tbl[g] < sc) ? g + 1 : ((sc != sc) ? c.len - 1 : g);
 }
 
 // One pair of elements of a progressive slice (same arithmetic as apply_one in pic_latent.cu).

@@ -65,8 +65,8 @@ static int sm_count() {
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
-constexpr int kFusedMaxElems = 51200;   // 200 KiB keys + 8 KiB histogram + 16 KiB candidates + scratch <= 227 KiB
-constexpr int kScratchWords = 64;  // block_select uses [0,48)
+constexpr int kFusedMaxElems = 131072;  // one CTA per unit up to here; larger units take the multi-CTA rounds path
+constexpr int kScratchWords = 192;  // block_select uses [0,48); small-set helpers [44,192)
 constexpr int kTableSmem = 64;
 constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
 constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
@@ -82,7 +82,12 @@ struct SliceParams {
     float *thr_out, *a_out, *b_out;
     double *rate;
     int apply_kind;  // 0: select only, 1: mask only, 2: full slice
+    int use_stage;   // dynamic shared memory holds the cp.async stage buffer
 };
+
+// diagnostics: units whose sampled bracket missed (counted since library load)
+__device__ unsigned long long g_fallback_units = 0ull;
+__device__ unsigned long long g_sampled_units = 0ull;
 
 struct SelectState {
     uint32_t lo, hi;
@@ -107,36 +112,29 @@ __device__ __forceinline__ IndexCtx index_ctx_setup(const SliceParams &p, float 
     ic.len = p.table_len;
     ic.tbl64 = (p.table_len == kTableSmem) && p.idx;
     ic.tbl = p.table;
-    ic.pairs = nullptr;
     ic.geometric = false;
-    ic.lg2_t0 = 0.0f;
     ic.inv_step = 0.0f;
+    ic.bias = 0.0f;
     if (!ic.tbl64) return ic;  // uniform
     const int tid = threadIdx.x;
-    float2 *pairs = reinterpret_cast<float2 *>(sm + 64);
-    if (tid < kTableSmem) {
-        const float t = p.table[tid];
-        sm[tid] = t;
-        const float prev = (tid == 0) ? -INFINITY : p.table[tid - 1];
-        pairs[tid] = make_float2(prev, (tid == kTableSmem - 1) ? INFINITY : t);
-    }
+    if (tid < kTableSmem) sm[tid] = p.table[tid];
     if (tid == 0) {
         const float l0 = lg2_approx(p.table[0]);
         const float l1 = lg2_approx(p.table[kTableSmem - 1]);
+        const float inv = static_cast<float>(kTableSmem - 1) / (l1 - l0);
         sm[192] = l0;
-        sm[193] = static_cast<float>(kTableSmem - 1) / (l1 - l0);
+        sm[193] = inv;
     }
     __syncthreads();
     bool ok = true;
     if (tid < kTableSmem) {
         const float x = (lg2_approx(sm[tid]) - sm[192]) * sm[193];
-        ok = fabsf(x - static_cast<float>(tid)) < 0.25f;      // guess lands within +-1 of the answer
+        ok = fabsf(x - static_cast<float>(tid)) < 1e-3f;      // table is geometric to well within eps
     }
     const int all_ok = __syncthreads_and(ok ? 1 : 0);
     ic.tbl = sm;
-    ic.pairs = pairs;
-    ic.lg2_t0 = sm[192];
     ic.inv_step = sm[193];
+    ic.bias = -(sm[192] * sm[193] + 4e-3f);
     ic.geometric = all_ok != 0 && (sm[193] > 0.0f);
     return ic;
 }
@@ -144,48 +142,93 @@ __device__ __forceinline__ IndexCtx index_ctx_setup(const SliceParams &p, float 
 // Applies the slice arithmetic to elements [0, len) of a unit-local range starting at global
 // element offset `off`.  keys != nullptr: std comes from the shared-memory key tile (index 0 ==
 // first element of the range); otherwise from global memory.
-template <bool TRAIN, bool VEC, int THREADS>
+// OUTS: compile-time set of optional tensors (bit 0 y_base, 1 mask, 2 y_hat, 3 lik, 4 idx,
+// 5 symbols, 6 rate) or -1 = decided at run time from the pointers (generic flavour).
+constexpr int kOutsCodec = 0x1f;   // y_base + mask, y_hat, lik, idx   (compress / eval forward)
+constexpr int kOutsTrain = 0x0f;   // y_base + mask, y_hat, lik        (training forward)
+constexpr int kOutsGeneric = -1;
+
+__host__ __device__ inline int outs_of(const SliceParams &p) {
+    return (p.y_base ? 1 : 0) | (p.mask ? 2 : 0) | (p.y_hat ? 4 : 0) | (p.lik ? 8 : 0) | (p.idx ? 16 : 0) |
+           (p.symbols ? 32 : 0) | (p.rate ? 64 : 0);
+}
+
+template <bool TRAIN, bool VEC, int THREADS, int OUTS>
 __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, int len,
                                              const uint32_t *keys, int mode, float thr_in,
-                                             const IndexCtx &ic) {
+                                             const IndexCtx &ic, float4 *stage = nullptr) {
     float rate_acc = 0.0f;
     const int tid = threadIdx.x;
     const bool full = p.apply_kind == 2;
     const bool force_one = mode == kModeOnes;
     const float thr = (mode == kModeZeros) ? __int_as_float(0x7fc00000) : thr_in;  // s >= NaN is false
-    const bool has_base = p.y_base != nullptr;
-    const bool want_lik = (p.lik != nullptr) || (p.rate != nullptr);
-    const bool want_idx = p.idx != nullptr, want_sym = p.symbols != nullptr;
+    const int outs = (OUTS >= 0) ? OUTS : outs_of(p);
+    const bool has_base = outs & 1, want_mask = outs & 2, want_yhat = outs & 4;
+    const bool want_lik = outs & (8 | 64), store_lik = outs & 8;
+    const bool want_idx = outs & 16, want_sym = outs & 32, want_rate = outs & 64;
     if (VEC) {
         const int nvec = len >> 2;
-        const float4 *std4 = reinterpret_cast<const float4 *>(p.std + off);
-        const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top + off);
-        const float4 *yb4 = has_base ? reinterpret_cast<const float4 *>(p.y_base + off) : nullptr;
-        const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu + off);
-        const float4 *nz4 = TRAIN ? reinterpret_cast<const float4 *>(p.noise + off) : nullptr;
+        const uint64_t pol_first = policy_evict_first();
+        // one 32-bit vector index for every tensor (host guarantees total elements < 2^34)
+        const uint32_t vbase = static_cast<uint32_t>(off >> 2);
+        const float4 *std4 = reinterpret_cast<const float4 *>(p.std);
+        const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top);
+        const float4 *yb4 = reinterpret_cast<const float4 *>(p.y_base);
+        const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu);
+        const float4 *nz4 = reinterpret_cast<const float4 *>(p.noise);
         const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
-        for (int j = tid; j < nvec; j += THREADS) {
+        // Software pipeline: with a stage buffer the inputs of iteration i+1 are copied
+        // global->shared (cp.async, per-thread private 16-byte slots: no barrier needed) while
+        // iteration i is computed, so ~2x the bytes are in flight per SM at no register cost.
+        constexpr int NARR = TRAIN ? 5 : 4;
+        const bool piped = (stage != nullptr) && full && (keys == nullptr);
+        auto slot = [&](int st, int arr) -> float4 * { return stage + (st * NARR + arr) * THREADS + tid; };
+        auto prefetch = [&](int jj, int st) {
+            const uint32_t v = vbase + static_cast<uint32_t>(jj);
+            cp_async16(slot(st, 0), std4 + v, pol_first);
+            cp_async16(slot(st, 1), yt4 + v, pol_first);
+            if (has_base) cp_async16(slot(st, 2), yb4 + v, pol_first);
+            cp_async16(slot(st, 3), mu4 + v, pol_first);
+            if (TRAIN) cp_async16(slot(st, NARR - 1), nz4 + v, pol_first);
+        };
+        if (piped && tid < nvec) prefetch(tid, 0);
+        if (piped) cp_async_commit();
+        int st = 0;
+        for (int j = tid; j < nvec; j += THREADS, st ^= 1) {
+            const uint32_t vi = vbase + static_cast<uint32_t>(j);
             float s[4];
-            if (keys) {
-                const uint4 k = k4[j];
-                s[0] = key_to_float(k.x); s[1] = key_to_float(k.y);
-                s[2] = key_to_float(k.z); s[3] = key_to_float(k.w);
-            } else {
-                const float4 v = __ldg(std4 + j);
+            float4 ytv, muv, ybv = make_float4(0.f, 0.f, 0.f, 0.f), nzv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (piped) {
+                if (j + THREADS < nvec) prefetch(j + THREADS, st ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();          // everything but the newest group has landed
+                const float4 v = *slot(st, 0);
                 s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-            }
-            if (!full) {
-                float mk[4];
+                ytv = *slot(st, 1);
+                if (has_base) ybv = *slot(st, 2);
+                muv = *slot(st, 3);
+                if (TRAIN) nzv = *slot(st, NARR - 1);
+            } else {
+                if (keys) {
+                    const uint4 k = k4[j];
+                    s[0] = key_to_float(k.x); s[1] = key_to_float(k.y);
+                    s[2] = key_to_float(k.z); s[3] = key_to_float(k.w);
+                } else {
+                    const float4 v = ld_hint(std4 + vi, pol_first);   // second (last) use of std: may leave L2
+                    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+                }
+                if (!full) {
+                    float mk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) mk[e] = ((s[e] >= thr) || force_one) ? 1.0f : 0.0f;
-                reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(mk[0], mk[1], mk[2], mk[3]);
-                continue;
+                    for (int e = 0; e < 4; ++e) mk[e] = ((s[e] >= thr) || force_one) ? 1.0f : 0.0f;
+                    reinterpret_cast<float4 *>(p.mask)[vi] = make_float4(mk[0], mk[1], mk[2], mk[3]);
+                    continue;
+                }
+                ytv = ld_hint(yt4 + vi, pol_first);
+                muv = ld_hint(mu4 + vi, pol_first);
+                if (has_base) ybv = ld_hint(yb4 + vi, pol_first);
+                if (TRAIN) nzv = ld_hint(nz4 + vi, pol_first);
             }
-            const float4 ytv = __ldg(yt4 + j);
-            const float4 muv = __ldg(mu4 + j);
-            float4 ybv = make_float4(0.f, 0.f, 0.f, 0.f), nzv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_base) ybv = __ldg(yb4 + j);
-            if (TRAIN) nzv = __ldg(nz4 + j);
             const float yt[4] = {ytv.x, ytv.y, ytv.z, ytv.w}, yb[4] = {ybv.x, ybv.y, ybv.z, ybv.w};
             const float mu[4] = {muv.x, muv.y, muv.z, muv.w}, nz[4] = {nzv.x, nzv.y, nzv.z, nzv.w};
             PairOut o[2];
@@ -193,14 +236,15 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
             for (int h = 0; h < 2; ++h) {
                 apply_pair<TRAIN>(s + 2 * h, yt + 2 * h, yb + 2 * h, mu + 2 * h, nz + 2 * h, has_base, thr,
                                   force_one, p.scale_bound, p.lik_bound, want_lik, want_idx, want_sym, ic, o[h]);
-                if (p.rate) rate_acc += logf(o[h].lik[0]) + logf(o[h].lik[1]);
+                if (want_rate) rate_acc += logf(o[h].lik[0]) + logf(o[h].lik[1]);
             }
-            if (p.mask) reinterpret_cast<float4 *>(p.mask + off)[j] = make_float4(o[0].m[0], o[0].m[1], o[1].m[0], o[1].m[1]);
-            if (p.y_hat) reinterpret_cast<float4 *>(p.y_hat + off)[j] = make_float4(o[0].y_hat[0], o[0].y_hat[1], o[1].y_hat[0], o[1].y_hat[1]);
-            if (p.lik) reinterpret_cast<float4 *>(p.lik + off)[j] = make_float4(o[0].lik[0], o[0].lik[1], o[1].lik[0], o[1].lik[1]);
-            if (want_idx) reinterpret_cast<int4 *>(p.idx + off)[j] = make_int4(o[0].idx[0], o[0].idx[1], o[1].idx[0], o[1].idx[1]);
-            if (want_sym) reinterpret_cast<int4 *>(p.symbols + off)[j] = make_int4(o[0].sym[0], o[0].sym[1], o[1].sym[0], o[1].sym[1]);
+            if (want_mask) st_hint(reinterpret_cast<float4 *>(p.mask) + vi, make_float4(o[0].m[0], o[0].m[1], o[1].m[0], o[1].m[1]), pol_first);
+            if (want_yhat) st_hint(reinterpret_cast<float4 *>(p.y_hat) + vi, make_float4(o[0].y_hat[0], o[0].y_hat[1], o[1].y_hat[0], o[1].y_hat[1]), pol_first);
+            if (store_lik) st_hint(reinterpret_cast<float4 *>(p.lik) + vi, make_float4(o[0].lik[0], o[0].lik[1], o[1].lik[0], o[1].lik[1]), pol_first);
+            if (want_idx) st_hint(reinterpret_cast<int4 *>(p.idx) + vi, make_int4(o[0].idx[0], o[0].idx[1], o[1].idx[0], o[1].idx[1]), pol_first);
+            if (want_sym) st_hint(reinterpret_cast<int4 *>(p.symbols) + vi, make_int4(o[0].sym[0], o[0].sym[1], o[1].sym[0], o[1].sym[1]), pol_first);
         }
+        if (piped) cp_async_wait<0>();
     } else {
         for (int j = tid; j < len; j += THREADS) {
             const float sv = keys ? key_to_float(keys[j]) : __ldg(p.std + off + j);
@@ -216,10 +260,10 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
             PairOut o;
             apply_pair<TRAIN>(s, yt, yb, mu, nz, has_base, thr, force_one, p.scale_bound, p.lik_bound, want_lik,
                               want_idx, want_sym, ic, o);
-            if (p.rate) rate_acc += logf(o.lik[0]);
-            if (p.mask) p.mask[off + j] = o.m[0];
-            if (p.y_hat) p.y_hat[off + j] = o.y_hat[0];
-            if (p.lik) p.lik[off + j] = o.lik[0];
+            if (want_rate) rate_acc += logf(o.lik[0]);
+            if (want_mask) p.mask[off + j] = o.m[0];
+            if (want_yhat) p.y_hat[off + j] = o.y_hat[0];
+            if (store_lik) p.lik[off + j] = o.lik[0];
             if (want_idx) p.idx[off + j] = o.idx[0];
             if (want_sym) p.symbols[off + j] = o.sym[0];
         }
@@ -244,21 +288,157 @@ __device__ __forceinline__ double block_sum_f64(float v, double *sh /* THREADS/3
 }
 
 // ------------------------------------------------------------------------------------------
-// fused kernel: one CTA per unit
+// fused kernel: one CTA per unit, several CTAs resident per SM
 // ------------------------------------------------------------------------------------------
-template <bool TRAIN, bool VEC, int THREADS>
-__global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = static_cast<int>(p.n);
-    const int n_pad = (n + 3) & ~3;
-    uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *hist = keys + n_pad;
-    uint32_t *cand = hist + kHistBins;
-    uint32_t *scratch = cand + kCandMax;
-    float *tbl = reinterpret_cast<float *>(scratch + kScratchWords);
-    double *red = reinterpret_cast<double *>(tbl + kIndexSmemFloats);
+// Sampled-pivot exact select (Floyd-Rivest style) of the two order statistics of one unit:
+//   1. S <= 4096 keys are sampled (strided with a hashed jitter) into shared memory,
+//   2. two sample order statistics bracketing the wanted rank by ~4 sigma become pivots,
+//   3. ONE streaming sweep over the unit's std (the only HBM read of std) counts the keys
+//      below the bracket and compacts the bracket (about n * 8 sigma / S keys) into `cand`,
+//   4. the exact ranks are found among the candidates with the shared-memory radix select.
+// Returns false (uniformly) when the bracket missed or overflowed; the caller then runs the
+// full histogram select.  NaN presence is reported through scratch[39].
+template <int THREADS, bool VEC>
+__device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32_t lo, uint32_t hi,
+                                               uint32_t *hist, uint32_t *cand, uint32_t *scratch,
+                                               uint32_t &a_key, uint32_t &b_key) {
     const int tid = threadIdx.x;
-    const IndexCtx ic = index_ctx_setup(p, tbl);
+    int S = n >> 3;
+    S = S < 1024 ? 1024 : (S > kCandMax ? kCandMax : S);
+    S &= ~3;
+    // ---- 1. sample ----------------------------------------------------------------------
+    if (VEC) {
+        const int nvec = n >> 2, S4 = S >> 2;
+        const int stride = nvec / S4;  // >= 1 because n > kCandMax >= S
+        const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
+        for (int i = tid; i < S4; i += THREADS) {
+            const uint32_t jit = ((static_cast<uint32_t>(i) * 0x9E3779B1u) >> 12) % static_cast<uint32_t>(stride);
+            const float4 v = __ldg(s4 + static_cast<size_t>(i) * stride + jit);
+            reinterpret_cast<uint4 *>(cand)[i] =
+                make_uint4(float_to_key(v.x), float_to_key(v.y), float_to_key(v.z), float_to_key(v.w));
+        }
+    } else {
+        const int stride = n / S;
+        for (int i = tid; i < S; i += THREADS) {
+            const uint32_t jit = ((static_cast<uint32_t>(i) * 0x9E3779B1u) >> 12) % static_cast<uint32_t>(stride);
+            cand[i] = float_to_key(__ldg(std_u + static_cast<size_t>(i) * stride + jit));
+        }
+    }
+    __syncthreads();
+    // ---- 2. pivots: sample ranks kt -+ 4 sigma, resolved together to 22-bit buckets --------
+    const float frac = static_cast<float>(lo) / static_cast<float>(n > 1 ? n - 1 : 1);
+    const float kt = frac * static_cast<float>(S - 1);
+    const float margin = 4.0f * sqrtf(static_cast<float>(S) * frac * (1.0f - frac)) + 4.0f;
+    const int klo = static_cast<int>(floorf(kt - margin));
+    const int khi = static_cast<int>(ceilf(kt + margin));
+    uint32_t plo_key, phi_key;
+    block_bracket_pair<THREADS>(cand, S, hist, scratch, klo > 0 ? klo : 0, khi < S - 1 ? khi : S - 1,
+                                plo_key, phi_key);
+    // open-ended bracket at the extremes of the sample; pivots as floats for the sweep
+    const float plo_f = (klo > 0) ? key_to_float(plo_key) : -INFINITY;
+    const float phi_f = (khi < S - 1) ? key_to_float(phi_key) : INFINITY;
+    if (tid == 0) { scratch[40] = 0u; scratch[41] = 0u; }
+    __syncthreads();  // cand (the sample) may now be overwritten
+    // ---- 3. sweep: count below, record the positions of the bracket's elements -------------
+    // float-domain compares (== key order for non-NaN, -0 == +0); NaN fails every compare.
+    uint32_t below = 0;
+    bool has_nan = false;
+    if (VEC) {
+        const int nvec = n >> 2;
+        const uint64_t pol_last = policy_evict_last();
+        const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
+        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
+            has_nan |= !(max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w)) == max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w)));
+            below += (q.x < plo_f) + (q.y < plo_f) + (q.z < plo_f) + (q.w < plo_f);
+            hits |= ((q.x >= plo_f && q.x <= phi_f) ? 1u : 0u) << sh;
+            hits |= ((q.y >= plo_f && q.y <= phi_f) ? 2u : 0u) << sh;
+            hits |= ((q.z >= plo_f && q.z <= phi_f) ? 4u : 0u) << sh;
+            hits |= ((q.w >= plo_f && q.w <= phi_f) ? 8u : 0u) << sh;
+        };
+        auto append = [&](uint32_t hits, int j0) {   // bit e -> element 4*(j0 + (e>>2)*THREADS) + (e&3)
+            if (hits == 0u) return;
+            uint32_t pos = atomicAdd(&scratch[40], static_cast<uint32_t>(__popc(hits)));
+            while (hits) {
+                const int e = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                if (pos < static_cast<uint32_t>(kCandMax))
+                    cand[pos] = (static_cast<uint32_t>(j0 + (e >> 2) * THREADS) << 2) | static_cast<uint32_t>(e & 3);
+                ++pos;
+            }
+        };
+        int j = tid;
+        for (; j + 3 * THREADS < nvec; j += 4 * THREADS) {   // 4 independent 128-bit loads in flight
+            const float4 v0 = ld_hint(s4 + j, pol_last), v1 = ld_hint(s4 + j + THREADS, pol_last);
+            const float4 v2 = ld_hint(s4 + j + 2 * THREADS, pol_last), v3 = ld_hint(s4 + j + 3 * THREADS, pol_last);
+            uint32_t hits = 0;
+            classify(v0, hits, 0); classify(v1, hits, 4); classify(v2, hits, 8); classify(v3, hits, 12);
+            append(hits, j);
+        }
+        for (; j < nvec; j += THREADS) {
+            const float4 v0 = ld_hint(s4 + j, pol_last);
+            uint32_t hits = 0;
+            classify(v0, hits, 0);
+            append(hits, j);
+        }
+    } else {
+        for (int j = tid; j < n; j += THREADS) {
+            const float x = __ldg(std_u + j);
+            has_nan |= (x != x);
+            below += (x < plo_f) ? 1u : 0u;
+            if (x >= plo_f && x <= phi_f) {
+                const uint32_t pos = atomicAdd(&scratch[40], 1u);
+                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = static_cast<uint32_t>(j);
+            }
+        }
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    if ((tid & 31) == 0 && below) atomicAdd(&scratch[41], below);
+    if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
+    __syncthreads();
+    const uint32_t c_cand = scratch[40], c_below = scratch[41];
+    // ---- 4. exact ranks among the candidates ------------------------------------------------
+    const bool valid = c_cand <= static_cast<uint32_t>(kCandMax) && c_below <= lo && hi < c_below + c_cand;
+    if (!valid) {
+        __syncthreads();
+        return false;
+    }
+    for (int i = tid; i < static_cast<int>(c_cand); i += THREADS)   // positions -> keys (L2 hits)
+        cand[i] = float_to_key(__ldg(std_u + cand[i]));
+    __syncthreads();
+    const uint32_t base = float_to_key(plo_f);
+    const uint32_t width = float_to_key(phi_f) - base;
+    block_select_norm<THREADS>(cand, static_cast<int>(c_cand), base, 32 - __clz(width | 1u), hist, scratch,
+                               lo - c_below, hi - c_below, a_key, b_key);
+    return true;
+}
+
+template <int THREADS>
+struct FusedSmem {
+    uint32_t scratch[kScratchWords];
+    float index[kIndexSmemFloats];
+    double red[THREADS / 32];
+};
+
+// dynamic shared memory: max(select buffers, cp.async stage buffer) -- the two are never live
+// at the same time (select finishes before the unit's apply sweep starts)
+constexpr size_t kSelectSmemBytes = (2 * kHistBins + kCandMax) * sizeof(uint32_t);
+template <bool TRAIN, int THREADS>
+constexpr size_t fused_dyn_smem() {
+    const size_t stage = size_t(2) * (TRAIN ? 5 : 4) * THREADS * sizeof(float4);
+    return stage > kSelectSmemBytes ? stage : kSelectSmemBytes;
+}
+
+template <bool TRAIN, bool VEC, int THREADS, int OUTS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) slice_fused_kernel(const SliceParams p) {
+    __shared__ __align__(16) FusedSmem<THREADS> sm;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float4 *stage = p.use_stage ? reinterpret_cast<float4 *>(dyn_smem) : nullptr;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(dyn_smem);
+    uint32_t *cand = hist + 2 * kHistBins;
+    uint32_t *scratch = sm.scratch;
+    const int n = static_cast<int>(p.n);
+    const int tid = threadIdx.x;
+    const IndexCtx ic = index_ctx_setup(p, sm.index);
 
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int64_t off = u * p.n;
@@ -266,59 +446,36 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
         const int mode = unit_mode(q);
         float thr = (mode == kModeOnes) ? -INFINITY : INFINITY;
         float a_val = thr, b_val = thr;
-        bool staged = false;
         if (p.thr_in && mode == kModeThreshold) {
             thr = p.thr_in[u];
             a_val = b_val = thr;
         } else if (mode == kModeThreshold) {
-            // ---- sweep 1: std -> keys in smem, round-0 histogram, NaN flag --------------
-            for (int j = tid; j < kHistBins; j += THREADS) hist[j] = 0u;
             if (tid == 0) scratch[39] = 0u;
             __syncthreads();
-            bool has_nan = false;
-            if (VEC) {
-                const float4 *std4 = reinterpret_cast<const float4 *>(p.std + off);
-                const int nvec = n >> 2;
-                for (int jb = tid - (tid & 31); jb < nvec; jb += THREADS) {
-                    const int j = jb + (tid & 31);
-                    const bool inb = j < nvec;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inb) v = __ldg(std4 + j);
-                    has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-                    const uint32_t k0 = float_to_key(v.x), k1 = float_to_key(v.y);
-                    const uint32_t k2 = float_to_key(v.z), k3 = float_to_key(v.w);
-                    const uint32_t d0 = k0 >> 21, d1 = k1 >> 21, d2 = k2 >> 21, d3 = k3 >> 21;
-                    // flat regions (128 consecutive values in one bin) are common in real std maps:
-                    // one atomic for the warp instead of 128 same-address ones
-                    const uint32_t lead = __shfl_sync(0xffffffffu, d0, 0);
-                    const bool run = __all_sync(0xffffffffu, inb && ((d0 ^ lead) | (d1 ^ lead) | (d2 ^ lead) | (d3 ^ lead)) == 0u);
-                    if (run) {
-                        if ((tid & 31) == 0) atomicAdd(&hist[lead], 128u);
-                    } else if (inb) {
-                        atomicAdd(&hist[d0], 1u);
-                        atomicAdd(&hist[d1], 1u);
-                        atomicAdd(&hist[d2], 1u);
-                        atomicAdd(&hist[d3], 1u);
-                    }
-                    if (inb) reinterpret_cast<uint4 *>(keys)[j] = make_uint4(k0, k1, k2, k3);
-                }
-            } else {
-                for (int j = tid; j < n; j += THREADS) {
-                    const float sv = __ldg(p.std + off + j);
-                    has_nan |= (sv != sv);
-                    const uint32_t k = float_to_key(sv);
-                    atomicAdd(&hist[k >> 21], 1u);
-                    keys[j] = k;
-                }
-            }
-            if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
-            __syncthreads();
-            staged = true;
             uint32_t lo, hi;
             float w;
             quantile_ranks(q, p.n, lo, hi, w);
-            uint32_t a_key, b_key;
-            block_select<THREADS>(keys, n, hist, cand, scratch, lo, hi, true, a_key, b_key);
+            uint32_t a_key = 0, b_key = 0;
+            const float *std_u = p.std + off;
+            if (n <= kCandMax) {
+                // small unit: all keys are candidates
+                bool has_nan = false;
+                for (int j = tid; j < n; j += THREADS) {
+                    const float v = __ldg(std_u + j);
+                    has_nan |= (v != v);
+                    cand[j] = float_to_key(v);
+                }
+                if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
+                __syncthreads();
+                block_select_norm<THREADS>(cand, n, 0u, 32, hist, scratch, lo, hi, a_key, b_key);
+            } else if (sampled_select<THREADS, VEC>(std_u, n, lo, hi, hist, cand, scratch, a_key, b_key)) {
+                if (tid == 0) atomicAdd(&g_sampled_units, 1ull);
+            } else {
+                if (tid == 0) atomicAdd(&g_fallback_units, 1ull);
+                // bracket missed or overflowed (heavy ties, adversarial order): full histogram select
+                // over the unit's std (L2-resident after the sweep)
+                block_select<THREADS, true>(GlobalStd{std_u, VEC}, n, hist, cand, scratch, lo, hi, false, a_key, b_key);
+            }
             a_val = key_to_float(a_key);
             b_val = key_to_float(b_key);
             thr = quantile_lerp(a_val, b_val, w);
@@ -330,13 +487,13 @@ __global__ void __launch_bounds__(THREADS) slice_fused_kernel(const SliceParams 
             if (p.b_out) p.b_out[u] = b_val;
         }
         if (p.apply_kind != 0) {
-            const float acc = apply_range<TRAIN, VEC, THREADS>(p, off, n, staged ? keys : nullptr, mode, thr, ic);
-            if (p.rate) {
-                const double total = block_sum_f64<THREADS>(acc, red);
+            const float acc = apply_range<TRAIN, VEC, THREADS, OUTS>(p, off, n, nullptr, mode, thr, ic, stage);
+            if ((OUTS >= 0) ? ((OUTS & 64) != 0) : (p.rate != nullptr)) {
+                const double total = block_sum_f64<THREADS>(acc, sm.red);
                 if (tid == 0) p.rate[u] = total;
             }
         }
-        __syncthreads();  // keys / hist are reused by the next unit
+        __syncthreads();  // hist / cand / scratch are reused by the next unit
     }
 }
 
@@ -488,7 +645,7 @@ __global__ void select_finish_kernel(const SelectState *state, const uint32_t *m
 // ------------------------------------------------------------------------------------------
 // apply with given thresholds: grid = units * tiles_per_unit
 // ------------------------------------------------------------------------------------------
-template <bool TRAIN, bool VEC>
+template <bool TRAIN, bool VEC, int OUTS>
 __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, int tiles_per_unit) {
     constexpr int THREADS = 256;
     __shared__ __align__(16) float tbl[kIndexSmemFloats];
@@ -503,7 +660,7 @@ __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, i
     if (tile == 0 && tid == 0 && p.thr_out) p.thr_out[u] = thr;
     const int64_t begin = static_cast<int64_t>(tile) * kApplyTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kApplyTile), p.n - begin));
-    const float acc = apply_range<TRAIN, VEC, THREADS>(p, u * p.n + begin, len, nullptr, mode, thr, ic);
+    const float acc = apply_range<TRAIN, VEC, THREADS, OUTS>(p, u * p.n + begin, len, nullptr, mode, thr, ic);
     if (p.rate) {
         const double total = block_sum_f64<THREADS>(acc, red);
         if (tid == 0) atomicAdd(&p.rate[u], total);
@@ -730,40 +887,37 @@ __global__ void __launch_bounds__(256) log_sum_kernel(const float *x, int64_t n_
 // ------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------
-static size_t fused_smem_bytes(int64_t n) {
-    const int64_t n_pad = (n + 3) & ~int64_t(3);
-    return static_cast<size_t>(n_pad) * 4 + kHistBins * 4 + kCandMax * 4 + kScratchWords * 4 + kIndexSmemFloats * 4 + 32 * 8;
-}
-
-template <bool TRAIN, bool VEC, int THREADS>
-static int launch_fused_t(const SliceParams &p, cudaStream_t stream) {
-    const size_t smem = fused_smem_bytes(p.n);
-    auto kern = slice_fused_kernel<TRAIN, VEC, THREADS>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured = 232448;
+template <bool TRAIN, bool VEC, int THREADS, int OUTS>
+static int launch_fused_t(const SliceParams &p_in, cudaStream_t stream) {
+    auto kern = slice_fused_kernel<TRAIN, VEC, THREADS, OUTS>;
+    SliceParams p = p_in;
+    p.use_stage = (VEC && p.apply_kind == 2) ? 1 : 0;
+    const size_t smem = fused_dyn_smem<TRAIN, THREADS>();
+    static bool configured = false;  // per instantiation
+    static int occ_blocks[2] = {0, 0};
+    if (!configured) {
+        PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
     }
-    static size_t occ_smem = ~size_t(0);
-    static int occ_blocks = 1;
-    if (smem != occ_smem) {
+    int &occ = occ_blocks[p.use_stage];
+    if (occ == 0) {
         int q = 1;
         PIC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));
-        occ_blocks = q < 1 ? 1 : q;
-        occ_smem = smem;
+        occ = q < 1 ? 1 : q;
     }
-    const int per_sm = occ_blocks;
-    const int64_t max_grid = static_cast<int64_t>(sm_count()) * per_sm;
+    const int64_t max_grid = static_cast<int64_t>(sm_count()) * occ;
     const int grid = static_cast<int>(p.units < max_grid ? p.units : max_grid);
     kern<<<grid, THREADS, smem, stream>>>(p);
     return launch_status();
 }
 
-template <bool TRAIN, bool VEC>
+template <bool TRAIN, bool VEC, int OUTS>
 static int launch_fused_v(const SliceParams &p, cudaStream_t stream) {
-    if (p.n > 16384) return launch_fused_t<TRAIN, VEC, 1024>(p, stream);
-    if (p.n > 4096) return launch_fused_t<TRAIN, VEC, 512>(p, stream);
-    return launch_fused_t<TRAIN, VEC, 256>(p, stream);
+    // few large units: wider CTAs finish each unit sooner; otherwise 4 x 256-thread CTAs per SM
+    // give the best overlap of one unit's (latency-bound) select with other units' apply sweeps
+    if (p.n > 16384 && p.units < 2 * static_cast<int64_t>(sm_count()))
+        return launch_fused_t<TRAIN, VEC, 512, OUTS>(p, stream);
+    return launch_fused_t<TRAIN, VEC, 256, OUTS>(p, stream);
 }
 
 static bool slice_vec_ok(const SliceParams &p) {
@@ -774,29 +928,77 @@ static bool slice_vec_ok(const SliceParams &p) {
     return true;
 }
 
+// the vectorised kernels index every tensor with one 32-bit float4 index
+constexpr int64_t kMaxElemsPerLaunch = int64_t(1) << 33;
+
+template <bool TRAIN>
+static int launch_fused_f(const SliceParams &p, bool vec, cudaStream_t stream) {
+    if (!vec) return launch_fused_v<TRAIN, false, kOutsGeneric>(p, stream);
+    const int outs = (p.apply_kind == 2) ? outs_of(p) : -2;
+    if (outs == kOutsCodec) return launch_fused_v<TRAIN, true, kOutsCodec>(p, stream);
+    if (outs == kOutsTrain) return launch_fused_v<TRAIN, true, kOutsTrain>(p, stream);
+    return launch_fused_v<TRAIN, true, kOutsGeneric>(p, stream);
+}
+
+static SliceParams slice_units(const SliceParams &p, int64_t u0, int64_t count) {
+    SliceParams q = p;
+    const int64_t e = u0 * p.n;
+    q.units = count;
+    q.y_top = p.y_top ? p.y_top + e : nullptr;  q.y_base = p.y_base ? p.y_base + e : nullptr;
+    q.mu = p.mu ? p.mu + e : nullptr;            q.std = p.std ? p.std + e : nullptr;
+    q.noise = p.noise ? p.noise + e : nullptr;   q.mask = p.mask ? p.mask + e : nullptr;
+    q.y_hat = p.y_hat ? p.y_hat + e : nullptr;   q.lik = p.lik ? p.lik + e : nullptr;
+    q.idx = p.idx ? p.idx + e : nullptr;         q.symbols = p.symbols ? p.symbols + e : nullptr;
+    q.q01_per_unit = p.q01_per_unit ? p.q01_per_unit + u0 : nullptr;
+    q.thr_in = p.thr_in ? p.thr_in + u0 : nullptr;
+    q.thr_out = p.thr_out ? p.thr_out + u0 : nullptr;
+    q.a_out = p.a_out ? p.a_out + u0 : nullptr;  q.b_out = p.b_out ? p.b_out + u0 : nullptr;
+    q.rate = p.rate ? p.rate + u0 : nullptr;
+    return q;
+}
+
 static int launch_fused(const SliceParams &p, cudaStream_t stream) {
     const bool vec = slice_vec_ok(p);
     const bool train = p.noise != nullptr && p.apply_kind == 2;
-    if (train) return vec ? launch_fused_v<true, true>(p, stream) : launch_fused_v<true, false>(p, stream);
-    return vec ? launch_fused_v<false, true>(p, stream) : launch_fused_v<false, false>(p, stream);
+    const int64_t max_units = kMaxElemsPerLaunch / p.n;
+    for (int64_t u0 = 0; u0 < p.units; u0 += max_units) {
+        const int64_t cnt = (p.units - u0 < max_units) ? (p.units - u0) : max_units;
+        const SliceParams q = (u0 == 0 && cnt == p.units) ? p : slice_units(p, u0, cnt);
+        const int rc = train ? launch_fused_f<true>(q, vec, stream) : launch_fused_f<false>(q, vec, stream);
+        if (rc != PIC_OK) return rc;
+    }
+    return PIC_OK;
+}
+
+template <bool TRAIN>
+static int launch_apply_f(const SliceParams &p, bool vec, int grid, int tiles, cudaStream_t stream) {
+    if (!vec) {
+        slice_apply_kernel<TRAIN, false, kOutsGeneric><<<grid, 256, 0, stream>>>(p, tiles);
+    } else {
+        const int outs = (p.apply_kind == 2) ? outs_of(p) : -2;
+        if (outs == kOutsCodec) slice_apply_kernel<TRAIN, true, kOutsCodec><<<grid, 256, 0, stream>>>(p, tiles);
+        else if (outs == kOutsTrain) slice_apply_kernel<TRAIN, true, kOutsTrain><<<grid, 256, 0, stream>>>(p, tiles);
+        else slice_apply_kernel<TRAIN, true, kOutsGeneric><<<grid, 256, 0, stream>>>(p, tiles);
+    }
+    return launch_status();
 }
 
 static int launch_apply(const SliceParams &p, cudaStream_t stream) {
     const bool vec = slice_vec_ok(p);
     const bool train = p.noise != nullptr && p.apply_kind == 2;
     const int tiles = static_cast<int>((p.n + kApplyTile - 1) / kApplyTile);
-    const int64_t grid64 = p.units * tiles;
-    if (grid64 > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
-    const int grid = static_cast<int>(grid64);
     if (p.rate) PIC_CUDA_CHECK(cudaMemsetAsync(p.rate, 0, sizeof(double) * p.units, stream));
-    if (train) {
-        if (vec) slice_apply_kernel<true, true><<<grid, 256, 0, stream>>>(p, tiles);
-        else slice_apply_kernel<true, false><<<grid, 256, 0, stream>>>(p, tiles);
-    } else {
-        if (vec) slice_apply_kernel<false, true><<<grid, 256, 0, stream>>>(p, tiles);
-        else slice_apply_kernel<false, false><<<grid, 256, 0, stream>>>(p, tiles);
+    const int64_t max_units = kMaxElemsPerLaunch / p.n < 1 ? 1 : kMaxElemsPerLaunch / p.n;
+    for (int64_t u0 = 0; u0 < p.units; u0 += max_units) {
+        const int64_t cnt = (p.units - u0 < max_units) ? (p.units - u0) : max_units;
+        const SliceParams q = (u0 == 0 && cnt == p.units) ? p : slice_units(p, u0, cnt);
+        const int64_t grid64 = cnt * tiles;
+        if (grid64 > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
+        const int rc = train ? launch_apply_f<true>(q, vec, static_cast<int>(grid64), tiles, stream)
+                             : launch_apply_f<false>(q, vec, static_cast<int>(grid64), tiles, stream);
+        if (rc != PIC_OK) return rc;
     }
-    return launch_status();
+    return PIC_OK;
 }
 
 // workspace layout of the multi-launch select: [state][hist x3 rounds][min_above]
@@ -914,6 +1116,13 @@ const char *pic_error_string(int code) {
 int pic_last_cuda_error(void) { return g_last_cuda_error; }
 
 int64_t pic_fused_max_elems(void) { return kFusedMaxElems; }
+
+int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback) {
+    PIC_CUDA_CHECK(cudaDeviceSynchronize());
+    PIC_CUDA_CHECK(cudaMemcpyFromSymbol(sampled, g_sampled_units, sizeof(unsigned long long)));
+    PIC_CUDA_CHECK(cudaMemcpyFromSymbol(fallback, g_fallback_units, sizeof(unsigned long long)));
+    return PIC_OK;
+}
 
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units) {
     if (n_per_unit <= kFusedMaxElems || units <= 0) return 256;  // fused path needs none; keep non-zero

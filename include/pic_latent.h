@@ -66,6 +66,10 @@ int pic_last_cuda_error(void); /* cudaError_t of the last failing runtime call o
  * shared memory between select and apply); larger units take the multi-launch path. */
 int64_t pic_fused_max_elems(void);
 
+/* Diagnostics (synchronises the device): number of units served by the sampled-pivot select and
+ * number that fell back to the full histogram select, since the library was loaded. */
+int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback);
+
 /* Scratch needed by pic_select_threshold / pic_channel_mask / pic_slice_forward. */
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units);
 
