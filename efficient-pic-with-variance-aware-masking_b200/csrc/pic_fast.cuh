@@ -101,9 +101,13 @@ __device__ __forceinline__ void st_hint(int4 *p, int4 v, uint64_t pol) {
 }
 
 // 16-byte asynchronous global->shared copy (LDGSTS) with an L2 policy; per-thread private slots
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, uint64_t pol) {
-    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "l"(pol) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gmem_src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t smem_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+    return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -180,9 +184,10 @@ struct IndexCtx {
 // fminf() maps NaN / huge sc to the last index (non-propagating min returns the other operand).
 __device__ __forceinline__ int scale_index_fast(float sc, const IndexCtx &c) {
     if (!c.geometric) return c.tbl64 ? scale_index64(sc, 0.0f, c.tbl) : scale_index(sc, 0.0f, c.tbl, c.len);
-    const float x = fminf(__fmaf_rn(lg2_approx(sc), c.inv_step, c.bias), static_cast<float>(c.len) - 1.5f);
+    // cap at len-2.5 so that g <= len-2 is always a valid table index; branch-free fix-up.
+    const float x = fminf(__fmaf_rn(lg2_approx(sc), c.inv_step, c.bias), static_cast<float>(c.len) - 2.5f);
     const int g = max(__float2int_rd(x) + 1, 0);
-    return (g < c.len - 1 && c.tbl[g] < sc) ? g + 1 : ((sc != sc) ? c.len - 1 : g);
+    return g + (!(sc <= c.tbl[g]) ? 1 : 0);   // !(<=) is also true for NaN -> len-1, like the reference
 }
 
 // One pair of elements of a progressive slice (same arithmetic as apply_one in pic_latent.cu).

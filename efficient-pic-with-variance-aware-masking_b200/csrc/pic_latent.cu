@@ -182,14 +182,17 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
         // iteration i is computed, so ~2x the bytes are in flight per SM at no register cost.
         constexpr int NARR = TRAIN ? 5 : 4;
         const bool piped = (stage != nullptr) && full && (keys == nullptr);
-        auto slot = [&](int st, int arr) -> float4 * { return stage + (st * NARR + arr) * THREADS + tid; };
+        // slot(st, arr) = sbase + st * kStageBytes + arr * kArrBytes (32-bit shared addresses)
+        constexpr uint32_t kArrBytes = THREADS * sizeof(float4), kStageBytes = NARR * kArrBytes;
+        const uint32_t sbase = piped ? static_cast<uint32_t>(__cvta_generic_to_shared(stage + tid)) : 0u;
         auto prefetch = [&](int jj, int st) {
             const uint32_t v = vbase + static_cast<uint32_t>(jj);
-            cp_async16(slot(st, 0), std4 + v, pol_first);
-            cp_async16(slot(st, 1), yt4 + v, pol_first);
-            if (has_base) cp_async16(slot(st, 2), yb4 + v, pol_first);
-            cp_async16(slot(st, 3), mu4 + v, pol_first);
-            if (TRAIN) cp_async16(slot(st, NARR - 1), nz4 + v, pol_first);
+            const uint32_t sa = sbase + (st ? kStageBytes : 0u);
+            cp_async16(sa, std4 + v, pol_first);
+            cp_async16(sa + kArrBytes, yt4 + v, pol_first);
+            if (has_base) cp_async16(sa + 2 * kArrBytes, yb4 + v, pol_first);
+            cp_async16(sa + 3 * kArrBytes, mu4 + v, pol_first);
+            if (TRAIN) cp_async16(sa + (NARR - 1) * kArrBytes, nz4 + v, pol_first);
         };
         if (piped && tid < nvec) prefetch(tid, 0);
         if (piped) cp_async_commit();
@@ -202,12 +205,13 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
                 if (j + THREADS < nvec) prefetch(j + THREADS, st ^ 1);
                 cp_async_commit();
                 cp_async_wait<1>();          // everything but the newest group has landed
-                const float4 v = *slot(st, 0);
+                const uint32_t sa = sbase + (st ? kStageBytes : 0u);
+                const float4 v = lds128(sa);
                 s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-                ytv = *slot(st, 1);
-                if (has_base) ybv = *slot(st, 2);
-                muv = *slot(st, 3);
-                if (TRAIN) nzv = *slot(st, NARR - 1);
+                ytv = lds128(sa + kArrBytes);
+                if (has_base) ybv = lds128(sa + 2 * kArrBytes);
+                muv = lds128(sa + 3 * kArrBytes);
+                if (TRAIN) nzv = lds128(sa + (NARR - 1) * kArrBytes);
             } else {
                 if (keys) {
                     const uint4 k = k4[j];
