@@ -3,15 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on host cores
-    torchrun --nproc-per-node N bench.py --gpus N ...        # N>1: one rank per GPU, units sharded, no collective
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N>1: one rank per GPU
 
-Default workload = BASELINE config[1]: Kodak-shape 768x512 latents ([1,32,32,48] => n=49152 per
-unit), 10 progressive slices x 101-point quality sweep (pr = 0, 0.1, .. 10) = 1010 units per step.
-A step launches the fused slice kernel once per slice index (10 launches of 101 units: slices are
-sequential in the codec, the quality sweep is the batch).  Inputs of a step are 794 MB (> 126 MB L2),
-so consecutive steps stream from HBM without an explicit L2 flush.
-
-One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+Workloads (--workload):
+  kodak_sweep (default, BASELINE config[1]): Kodak-shape 768x512 latents ([1,32,32,48] => n=49152 per
+      unit), 10 progressive slices x 101-point quality sweep (pr = 0, 0.1, .. 10) = 1010 units per step,
+      codec outputs (mask, y_hat, likelihood, scale index).  One step = ONE launch of the fused kernel over
+      all 1010 (slice, quality) units (--launch per_slice: one launch per slice index).  Weak scaling:
+      every rank runs a full replica on its own data, no collective on the data path.
+  first_train (config[2]): [256,32,16,16] x 10 slices, random quality per image, training-mode forward
+      (noise) + fused backward.  Weak scaling, no collective.
+  tile8192 (config[4]): one 8192x8192 image, 10 slices of n=8388608, each rank holds a row band; the
+      per-slice threshold comes from NCCL all-reduced radix histograms.  Strong scaling.
+Inputs of one step are far larger than the 126 MB L2 (kodak_sweep: 794 MB), so consecutive steps stream
+from HBM without an explicit flush.  One JSON line is printed by rank 0 (keys: DESIGN.md "Measurement").
 """
 from __future__ import annotations
 
@@ -32,15 +37,20 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (n_per_unit, slices, q-points, description)
-    "kodak_sweep": dict(n=32 * 32 * 48, slices=10, prs=[10.0 * k / 100 for k in range(101)],
-                        desc="Kodak 768x512 batch 1, 10 progressive slices x 101-point quality sweep"),
-    "first_train": dict(n=32 * 16 * 16, slices=10, prs=None, batch=256,
-                        desc="256 crops of 256x256, 10 slices, random q per image (refine/rems sampling)"),
-    "tile8192": dict(n=32 * 512 * 512, slices=10, prs=[1.0],
-                     desc="single 8192x8192 image, 10 slices, q=1"),
+    "kodak_sweep": dict(n=32 * 32 * 48, slices=10, prs=[10.0 * k / 100 for k in range(101)], scaling="weak",
+                        desc="Kodak 768x512 batch 1, 10 progressive slices x 101-point quality sweep, codec outputs",
+                        bytes_per_elem=32,  # y_top, y_base, mu, std read once (std 2nd read from L2) + mask, y_hat, lik, idx
+                        ),
+    "first_train": dict(n=32 * 16 * 16, slices=10, prs=None, batch=256, scaling="weak",
+                        desc="256 crops of 256x256, 10 slices, random q per image, training forward + backward",
+                        bytes_per_elem=32 + 48,  # fwd: 5 in (incl. noise) + 3 out; bwd: 8 in + 4 out
+                        ),
+    "tile8192": dict(n=32 * 512 * 512, slices=10, prs=[1.0], scaling="strong",
+                     desc="single 8192x8192 image, 10 slices, q=1, row bands over the ranks, NCCL histogram all-reduce",
+                     bytes_per_elem=36,  # std read by the select rounds (>=1 pass from HBM) + the 32 of the apply
+                     ),
 }
-BYTES_PER_ELEM = 32  # y_top 4 + y_base 4 + mu 4 + std 4 (read once: tile kept in smem) + mask, y_hat, lik, idx 16
+METRIC = "mask+quantize+likelihood throughput"
 
 
 def peaks():
@@ -48,10 +58,10 @@ def peaks():
     if os.path.isfile(path):
         try:
             with open(path) as f:
-                return float(json.load(f)["hbm_gbs"]), "measured"
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -61,21 +71,17 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
-        self.thread = None
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
-        self.thread.start()
+        threading.Thread(target=self._read, daemon=True).start()
 
     def _read(self):
         for line in self.proc.stdout:
@@ -84,9 +90,9 @@ class ClockSampler:
     def stop(self, t0: float, t1: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        allsm, sm, smax, reasons = [], [], [], set()
         for ts, line in self.rows:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
@@ -96,15 +102,15 @@ class ClockSampler:
             except ValueError:
                 continue
             smax.append(mx)
-            if t0 - 0.05 <= ts <= t1 + 0.15:
+            allsm.append(clk)
+            if t0 <= ts <= t1 + 0.03:
                 sm.append(clk)
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        if not sm:  # timed region shorter than the sampling period: use all samples
-            sm = [float(l.split(",")[0]) for _, l in self.rows if l and l.split(",")[0].strip().replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = sm if sm else allsm
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples_in_timed_region": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------ inputs
@@ -140,70 +146,74 @@ def unit_prs(wl, units_per_slice, seed):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_throughput(wl, seconds_budget, threads=None, sample_units=None):
+def cpu_sample(wl, cores):
+    """Bounded sample of the workload for the CPU arm: same unit size, a few units per host thread."""
+    n = wl["n"]
+    per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
+    total = per_slice * wl["slices"]
+    sample_units = max(1, min(total, max(cores * 2, (4 << 20) // n)))
+    if n > (1 << 20):
+        sample_units = 1          # one 8M-element unit is ~1 s of qsort per pass
+    prs_all = unit_prs(wl, per_slice, 4321)
+    prs = [prs_all[u % len(prs_all)] for u in range(sample_units)]
+    return sample_units, prs
+
+
+def cpu_pass(po, wl, arrays, prs, table):
+    y_top, y_base, mu, std = arrays
+    po.slice_forward(y_top, y_base, mu, std, prs, table, want=("mask", "y_hat", "lik", "idx"))
+
+
+def cpu_reference_throughput(wl, seconds_budget):
     """Times the oracle port (oracle/pic_oracle.c, OpenMP over units) on a bounded sample."""
     import pic_oracle as po
 
     po.build()
-    if threads:
-        po.set_num_threads(threads)
     cores = po.num_threads()
     n = wl["n"]
-    per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
-    if sample_units is None:
-        sample_units = max(1, min(per_slice * wl["slices"], max(cores * 2, (4 << 20) // n)))
-    prs_all = unit_prs(wl, per_slice, 4321)
-    prs = [prs_all[u % len(prs_all)] for u in range(sample_units)]
-    y_top, y_base, mu, std = make_host_inputs(n, sample_units, 99)
+    sample_units, prs = cpu_sample(wl, cores)
+    arrays = make_host_inputs(n, sample_units, 99)
     table = np.load(os.path.join(ROOT, "tests", "golden", "scale_table.npy"))
-    want = ("mask", "y_hat", "lik", "idx")
-    po.slice_forward(y_top, y_base, mu, std, prs, table, want=want)  # warm-up
-    times = []
-    t_start = time.perf_counter()
+    cpu_pass(po, wl, arrays, prs, table)  # warm-up
+    times, t_start = [], time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        po.slice_forward(y_top, y_base, mu, std, prs, table, want=want)
+        cpu_pass(po, wl, arrays, prs, table)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > seconds_budget or len(times) >= 50:
             break
     med = statistics.median(times)
-    gelem = sample_units * n / med / 1e9
-    return {"value": gelem, "unit": "Gelem/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_units} units x {n} elem, median of {len(times)} passes of oracle/pic_oracle.c "
-                      f"(qsort quantile + erfc + 63-step index), {cores} OpenMP threads"}, med, sample_units
+    return {"value": sample_units * n / med / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_units} units x {n} elem (forward, codec outputs), median of {len(times)} passes of "
+                      f"oracle/pic_oracle.c (qsort quantile + erfc + 63-step index), {cores} OpenMP threads"}
 
 
 def run_reference(args, wl):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     import pic_oracle as po
 
     po.build()
     cores = po.num_threads()
     n = wl["n"]
-    per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
-    sample_units = max(1, min(per_slice * wl["slices"], max(cores * 2, (4 << 20) // n)))
-    prs_all = unit_prs(wl, per_slice, 4321)
-    prs = [prs_all[u % len(prs_all)] for u in range(sample_units)]
-    y_top, y_base, mu, std = make_host_inputs(n, sample_units, 99)
+    sample_units, prs = cpu_sample(wl, cores)
+    arrays = make_host_inputs(n, sample_units, 99)
     table = np.load(os.path.join(ROOT, "tests", "golden", "scale_table.npy"))
-    want = ("mask", "y_hat", "lik", "idx")
     for _ in range(args.warmup):
-        po.slice_forward(y_top, y_base, mu, std, prs, table, want=want)
+        cpu_pass(po, wl, arrays, prs, table)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        po.slice_forward(y_top, y_base, mu, std, prs, table, want=want)
+        cpu_pass(po, wl, arrays, prs, table)
     dt = time.perf_counter() - t0
     value = args.steps * sample_units * n / dt / 1e9
-    sample = (f"each step = {sample_units} units x {n} elem of the {args.workload} workload through "
-              f"oracle/pic_oracle.c (C port of the reference's torch CPU path; the reference is Python and cannot "
-              f"travel to this box), {cores} OpenMP threads")
-    line = {"impl": "reference", "metric": "mask+quantize+likelihood throughput", "value": value, "unit": "Gelem/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n,
-                       "units_per_step": sample_units},
+    sample = (f"each step = {sample_units} units x {n} elem of the {args.workload} workload (forward, codec outputs) "
+              f"through oracle/pic_oracle.c, the C port of the reference's torch CPU path (the reference is Python "
+              f"and cannot travel to this box), {cores} OpenMP threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n,
+                                            "units_per_step": sample_units},
             "cpu_baseline": {"value": value, "unit": "Gelem/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -216,67 +226,103 @@ def run_cuda(args, wl):
     import torch.distributed as dist
 
     import pic_b200
+    from pic_b200 import distributed as pdist
     from pic_b200 import ops
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = pic_b200.lib()
-
+    name = args.workload
     n, slices = wl["n"], wl["slices"]
     per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
-    units = per_slice * slices                     # per rank (weak scaling: every rank runs a full replica)
+    units = per_slice * slices
     prs = unit_prs(wl, per_slice, 4321 + rank)
     seed = 1234 + 1000 * 2 + rank
-    y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
-    q_slice = ops.q01_tensor(prs, dev)
     table = pic_b200.get_scale_table().to(dev)
-    want = ("mask", "y_hat", "lik", "idx")
-    outs = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32, device=dev) for k in want}
-    ws_bytes = int(L.pic_workspace_bytes(n, per_slice))
-    fused = n <= int(L.pic_fused_max_elems())
-
-    def view(t, s):
-        return t[s * per_slice:(s + 1) * per_slice]
-
-    launches_per_step = [0]
-
+    q_slice = ops.q01_tensor(prs, dev)
     q_all = torch.cat([q_slice] * slices).contiguous()
+    fused = n <= int(L.pic_fused_max_elems())
+    launches = [0]
+    main_kernel = "slice_fused_kernel"
 
-    def step():
-        cnt = 0
-        if args.launch == "per_step":
-            ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
-            cnt = 1 if fused else 9
-        else:
-            for s in range(slices):
-                o = {k: view(v, s) for k, v in outs.items()}
-                ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice,
-                                  table, want=want, out=o)
-                cnt += 1 if fused else 9  # rounds path: begin + 3x(hist, advance) + finish + apply
-        launches_per_step[0] = cnt
+    if name == "tile8192":
+        # strong scaling: the unit is split into `world` row bands; every rank owns one band of each slice
+        n_local = n // world
+        y_top, y_base, mu, std = make_device_inputs(torch, n_local, units, seed, dev)
+        want = ("mask", "y_hat", "lik", "idx")
+        outs = {k: torch.empty((units, n_local), dtype=torch.int32 if k == "idx" else torch.float32, device=dev)
+                for k in want}
+        backend = pdist.CudaTileBackend(std, units) if world > 1 else None
+        main_kernel = "slice_apply_kernel" if (world == 1 or n_local > int(L.pic_fused_max_elems())) else "slice_fused_kernel"
+
+        def step():
+            if world == 1:
+                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
+                launches[0] = 9          # begin + 3 x (hist, advance) + finish + apply (+ 4 memsets, not kernels)
+            else:
+                thr = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
+                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr, want=want, out=outs)
+                launches[0] = 9          # same local kernels; + 4 NCCL all-reduces (not counted)
+        elems_per_rank = units * n_local
+        total_elems = units * n
+    elif name == "first_train":
+        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
+        g = torch.Generator(device=dev).manual_seed(seed + 7)
+        noise = torch.rand((units, n), device=dev, generator=g) - 0.5
+        g_lik = torch.randn((units, n), device=dev, generator=g)
+        g_yhat = torch.randn((units, n), device=dev, generator=g)
+        want = ("mask", "y_hat", "lik")
+        outs = {k: torch.empty((units, n), dtype=torch.float32, device=dev) for k in want}
+
+        def step():
+            ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)
+            ops.slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, outs["mask"], noise)
+            launches[0] = 2
+        elems_per_rank = units * n
+        total_elems = elems_per_rank * world
+    else:
+        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
+        want = ("mask", "y_hat", "lik", "idx")
+        outs = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32, device=dev)
+                for k in want}
+
+        def view(t, s):
+            return t[s * per_slice:(s + 1) * per_slice]
+
+        def step():
+            if args.launch == "per_step":
+                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
+                launches[0] = 1 if fused else 9
+            else:
+                for s in range(slices):
+                    o = {k: view(v, s) for k, v in outs.items()}
+                    ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice,
+                                      table, want=want, out=o)
+                launches[0] = slices * (1 if fused else 9)
+        elems_per_rank = units * n
+        total_elems = elems_per_rank * world
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
-    # repeat the K timed steps a few times so that the clock sampler sees the load; report the best-of
-    # is NOT done: the K steps are timed exactly once, the extra repetitions only feed the sampler.
+        time.sleep(0.1)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -293,16 +339,14 @@ def run_cuda(args, wl):
         ms = float(tms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = ms / args.steps
-    total_elems = units * n * world
     value = total_elems / (ms_per_step * 1e-3) / 1e9
 
-    # ---------------- end-to-end: host buffers through the C ABI (H2D + kernels + D2H timed) -------------
+    # ---------------- end-to-end: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ---
     e2e = None
-    if not args.no_e2e:
-        e2e_units = units
+    if not args.no_e2e and name == "kodak_sweep":
         chunk = max(1, min(per_slice, (48 << 20) // (n * 4)))
         host_in = [t.cpu().pin_memory() for t in (y_top, y_base, mu, std)]
-        q_host = torch.cat([q_slice.cpu()] * slices).pin_memory()
+        q_host = q_all.cpu().pin_memory()
         host_out = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32).pin_memory()
                     for k in want}
         nbytes = int(L.pic_host_pipeline_bytes(n, chunk))
@@ -313,7 +357,7 @@ def run_cuda(args, wl):
         def host_step():
             rc = L.pic_slice_forward_host(host_in[0].data_ptr(), host_in[1].data_ptr(), host_in[2].data_ptr(),
                                           host_in[3].data_ptr(), 0.5, q_host.data_ptr(), None, tb.data_ptr(), 64,
-                                          0.11, 1e-9, n, e2e_units, chunk, host_out["mask"].data_ptr(),
+                                          0.11, 1e-9, n, units, chunk, host_out["mask"].data_ptr(),
                                           host_out["y_hat"].data_ptr(), host_out["lik"].data_ptr(),
                                           host_out["idx"].data_ptr(), None, None, None, dbuf.data_ptr(), nbytes)
             if rc != 0:
@@ -324,55 +368,77 @@ def run_cuda(args, wl):
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            host_step()          # blocks until the outputs are in host memory
+            host_step()          # returns when the outputs are in host memory
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
             tdt = torch.tensor([dt], device=dev)
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
             dt = float(tdt.item())
-        e2e = {"value": e2e_units * n * world * e2e_steps / dt / 1e9, "unit": "Gelem/s",
-               "h2d_bytes_per_step": int(e2e_units * n * 16 + e2e_units * 4),
-               "d2h_bytes_per_step": int(e2e_units * n * 16), "steps": e2e_steps,
+        e2e = {"value": total_elems * e2e_steps / dt / 1e9, "unit": "Gelem/s",
+               "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 16),
+               "steps": e2e_steps, "per": "rank",
                "api": "pic_slice_forward_host (C ABI, pinned host buffers, 3-slot copy/compute pipeline)"}
-        # cheap sanity: the host path and the device path agree
         if rank == 0:
             assert torch.equal(host_out["mask"][:per_slice], outs["mask"][:per_slice].cpu()), "host/device mismatch"
 
+    # ---------------- roofline of the dominant kernel: CUDA events around that kernel alone ----------------
+    hbm, which = peaks()
+    roof = None
+    if rank == 0 or world > 1:
+        if name == "kodak_sweep" and args.launch == "per_step" and fused:
+            kern_ms, per_launch_elems = ms_per_step, units * n       # the step IS one launch of the kernel
+        else:
+            reps = 10
+            if name == "first_train":
+                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)  # noqa: E731
+                per_launch_elems = units * n
+            elif name == "tile8192":
+                thr0 = ops.select_threshold(std, units, q_all) if world == 1 else pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
+                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr0, want=want, out=outs)  # noqa: E731
+                per_launch_elems = elems_per_rank
+            else:
+                fn = lambda: ops.slice_forward(view(y_top, 0), view(y_base, 0), view(mu, 0), view(std, 0), per_slice, q_slice, table, want=want, out={k: view(v, 0) for k, v in outs.items()})  # noqa: E731
+                per_launch_elems = per_slice * n
+            fn()
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(reps):
+                fn()
+            k1.record()
+            torch.cuda.synchronize()
+            kern_ms = k0.elapsed_time(k1) / reps
+        kbytes = {"first_train": 32, "tile8192": 32}.get(name, wl["bytes_per_elem"])
+        bytes_per_launch = per_launch_elems * kbytes
+        achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(name)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": traffic, "peak_source": which, "kernel": main_kernel,
+                "algorithmic_bytes_per_elem": kbytes, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "launch_ms": kern_ms}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    hbm, which = peaks()
-    launches = launches_per_step[0] * args.steps
-    n_launch = 1 if args.launch == "per_step" else slices
-    kern_ms = ms_per_step / n_launch  # fused path: the step is n_launch back-to-back launches of one kernel
-    bytes_per_launch = units // n_launch * n * BYTES_PER_ELEM
-    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload)
-        except Exception:
-            traffic = None
-    cpu = None
-    if not args.no_cpu:
-        cpu, _, _ = cpu_reference_throughput(wl, args.cpu_seconds)
+    cpu = None if args.no_cpu else cpu_reference_throughput(wl, args.cpu_seconds)
     line = {
-        "metric": "mask+quantize+likelihood throughput", "value": value, "unit": "Gelem/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
-                   "units_per_launch": units if args.launch == "per_step" else per_slice, "launch": args.launch, "units_per_step_per_gpu": units, "launches_per_step": launches_per_step[0],
-                   "outputs": list(want), "bytes_per_elem": BYTES_PER_ELEM,
-                   "l2": f"inputs of one step = {units * n * 16 / 1e6:.0f} MB > 126 MB L2, no explicit flush",
-                   "parallelism": f"units sharded, {world} rank(s), no collective"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": traffic, "peak_source": which, "kernel": "slice_fused_kernel" if fused else "slice_apply_kernel",
-                     "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": kern_ms},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
+                   "units_per_step_per_gpu": units, "elements_per_step": total_elems, "launch": args.launch,
+                   "launches_per_step": launches[0], "outputs": list(want), "bytes_per_elem": wl["bytes_per_elem"],
+                   "l2": f"inputs of one step = {elems_per_rank * 16 / 1e6:.0f} MB per GPU > 126 MB L2, no explicit flush",
+                   "parallelism": (f"{world} rank(s), row-band tiles + NCCL histogram all-reduce" if name == "tile8192"
+                                   else f"{world} rank(s), units sharded, no collective")},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -382,12 +448,12 @@ def run_cuda(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
-                    help="per_step: all (slice, q) units of a step in one launch; per_slice: one launch per slice index")
+                    help="kodak_sweep: all (slice, q) units of a step in one launch, or one launch per slice index")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
