@@ -146,6 +146,14 @@ def unit_prs(wl, units_per_slice, seed):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; ignore that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(wl, cores):
     """Bounded sample of the workload for the CPU arm: same unit size, a few units per host thread."""
     n = wl["n"]
@@ -169,6 +177,7 @@ def cpu_reference_throughput(wl, seconds_budget):
     import pic_oracle as po
 
     po.build()
+    po.set_num_threads(host_threads())
     cores = po.num_threads()
     n = wl["n"]
     sample_units, prs = cpu_sample(wl, cores)
@@ -194,6 +203,7 @@ def run_reference(args, wl):
     import pic_oracle as po
 
     po.build()
+    po.set_num_threads(host_threads())
     cores = po.num_threads()
     n = wl["n"]
     sample_units, prs = cpu_sample(wl, cores)

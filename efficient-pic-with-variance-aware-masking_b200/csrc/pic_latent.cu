@@ -194,15 +194,19 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
             cp_async16(sa + 3 * kArrBytes, mu4 + v, pol_first);
             if (TRAIN) cp_async16(sa + (NARR - 1) * kArrBytes, nz4 + v, pol_first);
         };
-        if (piped && tid < nvec) prefetch(tid, 0);
+        // The sweep walks the unit BACKWARDS: in the fused kernel the select sweep has just read
+        // std front to back, so the tail of the unit is the part most likely still in L2.
+        const int iters = (nvec - tid + THREADS - 1) / THREADS;     // this thread's float4 count (may be <= 0)
+        const int jlast = tid + (iters - 1) * THREADS;
+        if (piped && iters > 0) prefetch(jlast, 0);
         if (piped) cp_async_commit();
         int st = 0;
-        for (int j = tid; j < nvec; j += THREADS, st ^= 1) {
+        for (int j = jlast; j >= 0; j -= THREADS, st ^= 1) {
             const uint32_t vi = vbase + static_cast<uint32_t>(j);
             float s[4];
             float4 ytv, muv, ybv = make_float4(0.f, 0.f, 0.f, 0.f), nzv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (piped) {
-                if (j + THREADS < nvec) prefetch(j + THREADS, st ^ 1);
+                if (j - THREADS >= 0) prefetch(j - THREADS, st ^ 1);
                 cp_async_commit();
                 cp_async_wait<1>();          // everything but the newest group has landed
                 const uint32_t sa = sbase + (st ? kStageBytes : 0u);
