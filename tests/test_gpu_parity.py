@@ -118,6 +118,34 @@ def test_slice_golden(pic, dev, case, mode):
             assert_grad_close(N(g), G[f"{tag}/{nm}"], f"{tag}/{nm}")
 
 
+@pytest.mark.parametrize("q_name,pr", [("pr2.5", 2.5), ("pr5", 5), ("pr10", 10)])
+def test_model_derived_config1(pic, dev, q_name, pr):
+    """BASELINE config[0]: latents captured from the random-init reference model (256x256 image, 10
+    progressive slices); drop-in classes composed exactly like models/pic.py:621-629, and the fused op."""
+    G = golden("model_c1.npz")
+    gc = pic.GaussianConditional(None)
+    gc.scale_table = torch.from_numpy(scale_table())
+    gc = gc.to(dev)
+    masking = pic.ChannelMask("point-based-std")
+    for k in range(10):
+        y_top, y_base = T(G[f"pr2.5/slice{k}/y_top"], dev), T(G[f"pr2.5/slice{k}/y_base"], dev)
+        mu, std = T(G[f"{q_name}/slice{k}/mu"], dev), T(G[f"{q_name}/slice{k}/std"], dev)
+        ref_mask = unpack_mask(G[f"{q_name}/slice{k}/mask"], std.shape)
+        # (a) the reference's own composition with the drop-in classes
+        y_slice = y_top - y_base
+        block_mask = masking.apply_noise(masking(std, pr=pr), False)
+        _, lik = gc((y_slice - mu) * block_mask, std * block_mask, training=False)
+        y_hat = pic.ste_round(y_slice - mu) * block_mask + mu
+        assert np.array_equal(N(block_mask), ref_mask), (q_name, k)
+        assert np.array_equal(N(y_hat), G[f"{q_name}/slice{k}/y_hat"]), (q_name, k)
+        assert_lik_close(N(lik), G[f"{q_name}/slice{k}/lik"], f"{q_name}/slice{k}")
+        # (b) the fused operator
+        out = pic.progressive_slice_forward(y_top, y_base, mu, std, pr, gc)
+        assert np.array_equal(N(out["mask"]), ref_mask), (q_name, k)
+        assert np.array_equal(N(out["y_hat"]), G[f"{q_name}/slice{k}/y_hat"]), (q_name, k)
+        assert_lik_close(N(out["likelihood"]), G[f"{q_name}/slice{k}/lik"], f"{q_name}/slice{k}/fused")
+
+
 @pytest.mark.parametrize("use_means", [False, True])
 @pytest.mark.parametrize("mode", ["eval", "train"])
 def test_gaussian_conditional_golden(pic, dev, use_means, mode):

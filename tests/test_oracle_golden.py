@@ -138,3 +138,20 @@ def test_build_indexes_quantize_kats():
     z = np.zeros((1, 8), np.float32)
     assert po.gaussian_forward(z, z)[1][0, 0] == G["kat/masked_lik"][0] == np.float32(0.9999945163726807)
     assert np.array_equal(G["kat/round"], np.asarray([0, 2, 2, -0.0, -2], np.float32))
+
+
+@pytest.mark.parametrize("q_name,pr", [("pr2.5", 2.5), ("pr5", 5), ("pr10", 10)])
+def test_model_derived_config1(q_name, pr):
+    """BASELINE config[0]: tensors captured from the random-init reference model on a 256x256 image
+    (oracle/gen_golden_model.py): the oracle reproduces what the reference's per-slice code produced."""
+    G = golden("model_c1.npz")
+    table = scale_table()
+    for k in range(10):
+        f = lambda a: a.reshape(1, -1)  # noqa: E731
+        y_top, y_base = G[f"pr2.5/slice{k}/y_top"], G[f"pr2.5/slice{k}/y_base"]
+        mu, std = G[f"{q_name}/slice{k}/mu"], G[f"{q_name}/slice{k}/std"]
+        assert std.shape == (1, 32, 16, 16)
+        o = po.slice_forward(f(y_top), f(y_base), f(mu), f(std), pr, table)
+        assert np.array_equal(o["mask"], unpack_mask(G[f"{q_name}/slice{k}/mask"], (1, std.size))), (q_name, k)
+        assert np.array_equal(o["y_hat"], f(G[f"{q_name}/slice{k}/y_hat"])), (q_name, k)
+        assert_lik_close(o["lik"], f(G[f"{q_name}/slice{k}/lik"]), f"{q_name}/slice{k}")
