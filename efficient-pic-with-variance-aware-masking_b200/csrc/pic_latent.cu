@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/pic_latent.h"
 #include "pic_math.cuh"
@@ -71,6 +72,8 @@ constexpr int kTableSmem = 64;
 constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
 constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
 constexpr int kRoundChunk = 16384;         // elements per CTA in hist_round_kernel
+constexpr int64_t kTwoKernelMinElems = int64_t(1) << 22;  // >= 4 Mi elements: select kernel + apply kernel
+constexpr int64_t kTwoKernelMinUnit = 32768;               // ... and units of at least this many elements
 
 struct SliceParams {
     const float *y_top, *y_base, *mu, *std, *q01_per_unit, *thr_in, *noise, *table;
@@ -147,6 +150,7 @@ __device__ __forceinline__ IndexCtx index_ctx_setup(const SliceParams &p, float 
 constexpr int kOutsCodec = 0x1f;   // y_base + mask, y_hat, lik, idx   (compress / eval forward)
 constexpr int kOutsTrain = 0x0f;   // y_base + mask, y_hat, lik        (training forward)
 constexpr int kOutsGeneric = -1;
+constexpr int kOutsSelectOnly = -3; // threshold selection only (no apply sweep compiled in)
 
 __host__ __device__ inline int outs_of(const SliceParams &p) {
     return (p.y_base ? 1 : 0) | (p.mask ? 2 : 0) | (p.y_hat ? 4 : 0) | (p.lik ? 8 : 0) | (p.idx ? 16 : 0) |
@@ -347,46 +351,80 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
     const float phi_f = (khi < S - 1) ? key_to_float(phi_key) : INFINITY;
     if (tid == 0) { scratch[40] = 0u; scratch[41] = 0u; }
     __syncthreads();  // cand (the sample) may now be overwritten
-    // ---- 3. sweep: count below, record the positions of the bracket's elements -------------
+    // ---- 3. sweep: count below, append the bracket's keys ------------------------------------
     // float-domain compares (== key order for non-NaN, -0 == +0); NaN fails every compare.
+    // Each iteration's values are parked in the (currently idle) histogram region of shared
+    // memory -- per-thread private float4 slots -- so a hit can be fetched by its bit index
+    // without dynamic register indexing and appended as a key right away.
     uint32_t below = 0;
     bool has_nan = false;
     if (VEC) {
+        constexpr int VPI = (THREADS <= 256) ? 4 : 2;            // float4 per thread per iteration (16 KB park area)
         const int nvec = n >> 2;
         const uint64_t pol_last = policy_evict_last();
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
+        float4 *park4 = reinterpret_cast<float4 *>(hist);
+        const float *park = reinterpret_cast<const float *>(hist) + tid * 4;
         auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
-            has_nan |= !(max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w)) == max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w)));
-            below += (q.x < plo_f) + (q.y < plo_f) + (q.z < plo_f) + (q.w < plo_f);
-            hits |= ((q.x >= plo_f && q.x <= phi_f) ? 1u : 0u) << sh;
-            hits |= ((q.y >= plo_f && q.y <= phi_f) ? 2u : 0u) << sh;
-            hits |= ((q.z >= plo_f && q.z <= phi_f) ? 4u : 0u) << sh;
-            hits |= ((q.w >= plo_f && q.w <= phi_f) ? 8u : 0u) << sh;
+            const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
+            has_nan |= (mx != mx);
+            below += (q.x < plo_f) ? 1u : 0u;
+            below += (q.y < plo_f) ? 1u : 0u;
+            below += (q.z < plo_f) ? 1u : 0u;
+            below += (q.w < plo_f) ? 1u : 0u;
+            if (q.x >= plo_f && q.x <= phi_f) hits |= 1u << sh;
+            if (q.y >= plo_f && q.y <= phi_f) hits |= 2u << sh;
+            if (q.z >= plo_f && q.z <= phi_f) hits |= 4u << sh;
+            if (q.w >= plo_f && q.w <= phi_f) hits |= 8u << sh;
         };
-        auto append = [&](uint32_t hits, int j0) {   // bit e -> element 4*(j0 + (e>>2)*THREADS) + (e&3)
-            if (hits == 0u) return;
-            uint32_t pos = atomicAdd(&scratch[40], static_cast<uint32_t>(__popc(hits)));
+        auto append = [&](uint32_t hits) {   // bit e -> park[(e >> 2) * THREADS * 4 + (e & 3)]
+            // one slot reservation per WARP (inclusive shuffle scan of the hit counts): the
+            // per-CTA counter would otherwise see ~2k serialised same-address atomics per unit
+            const uint32_t cnt = static_cast<uint32_t>(__popc(hits));
+            if (__ballot_sync(0xffffffffu, cnt != 0u) == 0u) return;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((tid & 31) >= d) incl += t;
+            }
+            uint32_t base = 0;
+            if ((tid & 31) == 31) base = atomicAdd(&scratch[40], incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t pos = base + incl - cnt;
             while (hits) {
                 const int e = __ffs(hits) - 1;
                 hits &= hits - 1u;
-                if (pos < static_cast<uint32_t>(kCandMax))
-                    cand[pos] = (static_cast<uint32_t>(j0 + (e >> 2) * THREADS) << 2) | static_cast<uint32_t>(e & 3);
+                const float x = park[(e >> 2) * (THREADS * 4) + (e & 3)];
+                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = float_to_key(x);
                 ++pos;
             }
         };
-        int j = tid;
-        for (; j + 3 * THREADS < nvec; j += 4 * THREADS) {   // 4 independent 128-bit loads in flight
-            const float4 v0 = ld_hint(s4 + j, pol_last), v1 = ld_hint(s4 + j + THREADS, pol_last);
-            const float4 v2 = ld_hint(s4 + j + 2 * THREADS, pol_last), v3 = ld_hint(s4 + j + 3 * THREADS, pol_last);
+        // warp-uniform trip counts (jb is the warp's first index): out-of-range lanes idle
+        const int lane = tid & 31;
+        int jb = tid - lane;
+        for (; jb + (VPI - 1) * THREADS + 31 < nvec; jb += VPI * THREADS) {   // VPI independent 128-bit loads in flight
+            const int j = jb + lane;
+            float4 v[VPI];
+#pragma unroll
+            for (int i = 0; i < VPI; ++i) v[i] = ld_hint(s4 + j + i * THREADS, pol_last);
             uint32_t hits = 0;
-            classify(v0, hits, 0); classify(v1, hits, 4); classify(v2, hits, 8); classify(v3, hits, 12);
-            append(hits, j);
+#pragma unroll
+            for (int i = 0; i < VPI; ++i) {
+                park4[i * THREADS + tid] = v[i];
+                classify(v[i], hits, 4 * i);
+            }
+            append(hits);
         }
-        for (; j < nvec; j += THREADS) {
-            const float4 v0 = ld_hint(s4 + j, pol_last);
+        for (; jb < nvec; jb += THREADS) {
+            const int j = jb + lane;
             uint32_t hits = 0;
-            classify(v0, hits, 0);
-            append(hits, j);
+            if (j < nvec) {
+                const float4 v0 = ld_hint(s4 + j, pol_last);
+                park4[tid] = v0;
+                classify(v0, hits, 0);
+            }
+            append(hits);
         }
     } else {
         for (int j = tid; j < n; j += THREADS) {
@@ -395,7 +433,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
             below += (x < plo_f) ? 1u : 0u;
             if (x >= plo_f && x <= phi_f) {
                 const uint32_t pos = atomicAdd(&scratch[40], 1u);
-                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = static_cast<uint32_t>(j);
+                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = float_to_key(x);
             }
         }
     }
@@ -410,9 +448,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         __syncthreads();
         return false;
     }
-    for (int i = tid; i < static_cast<int>(c_cand); i += THREADS)   // positions -> keys (L2 hits)
-        cand[i] = float_to_key(__ldg(std_u + cand[i]));
-    __syncthreads();
+    __syncthreads();   // the park area is the histogram: everyone must be done with it
     const uint32_t base = float_to_key(plo_f);
     const uint32_t width = float_to_key(phi_f) - base;
     block_select_norm<THREADS>(cand, static_cast<int>(c_cand), base, 32 - __clz(width | 1u), hist, scratch,
@@ -437,7 +473,8 @@ constexpr size_t fused_dyn_smem() {
 }
 
 template <bool TRAIN, bool VEC, int THREADS, int OUTS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) slice_fused_kernel(const SliceParams p) {
+__global__ void __launch_bounds__(THREADS, (OUTS == kOutsSelectOnly ? 1536 : 1024) / THREADS)
+slice_fused_kernel(const SliceParams p) {
     __shared__ __align__(16) FusedSmem<THREADS> sm;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4 *stage = p.use_stage ? reinterpret_cast<float4 *>(dyn_smem) : nullptr;
@@ -446,7 +483,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) slice_fused_kernel(co
     uint32_t *scratch = sm.scratch;
     const int n = static_cast<int>(p.n);
     const int tid = threadIdx.x;
-    const IndexCtx ic = index_ctx_setup(p, sm.index);
+    IndexCtx ic{};
+    if (OUTS != kOutsSelectOnly) ic = index_ctx_setup(p, sm.index);
 
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int64_t off = u * p.n;
@@ -494,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) slice_fused_kernel(co
             if (p.a_out) p.a_out[u] = a_val;
             if (p.b_out) p.b_out[u] = b_val;
         }
-        if (p.apply_kind != 0) {
+        if (OUTS != kOutsSelectOnly && p.apply_kind != 0) {
             const float acc = apply_range<TRAIN, VEC, THREADS, OUTS>(p, off, n, nullptr, mode, thr, ic, stage);
             if ((OUTS >= 0) ? ((OUTS & 64) != 0) : (p.rate != nullptr)) {
                 const double total = block_sum_f64<THREADS>(acc, sm.red);
@@ -900,7 +938,7 @@ static int launch_fused_t(const SliceParams &p_in, cudaStream_t stream) {
     auto kern = slice_fused_kernel<TRAIN, VEC, THREADS, OUTS>;
     SliceParams p = p_in;
     p.use_stage = (VEC && p.apply_kind == 2) ? 1 : 0;
-    const size_t smem = fused_dyn_smem<TRAIN, THREADS>();
+    const size_t smem = (OUTS == kOutsSelectOnly) ? kSelectSmemBytes : fused_dyn_smem<TRAIN, THREADS>();
     static bool configured = false;  // per instantiation
     static int occ_blocks[2] = {0, 0};
     if (!configured) {
@@ -923,7 +961,8 @@ template <bool TRAIN, bool VEC, int OUTS>
 static int launch_fused_v(const SliceParams &p, cudaStream_t stream) {
     // few large units: wider CTAs finish each unit sooner; otherwise 4 x 256-thread CTAs per SM
     // give the best overlap of one unit's (latency-bound) select with other units' apply sweeps
-    if (p.n > 16384 && p.units < 2 * static_cast<int64_t>(sm_count()))
+    static const int forced = [] { const char *e = getenv("PIC_FUSED_THREADS"); return e ? atoi(e) : 0; }();
+    if (forced == 512 || (forced == 0 && p.n > 16384 && p.units < 2 * static_cast<int64_t>(sm_count())))
         return launch_fused_t<TRAIN, VEC, 512, OUTS>(p, stream);
     return launch_fused_t<TRAIN, VEC, 256, OUTS>(p, stream);
 }
@@ -941,6 +980,8 @@ constexpr int64_t kMaxElemsPerLaunch = int64_t(1) << 33;
 
 template <bool TRAIN>
 static int launch_fused_f(const SliceParams &p, bool vec, cudaStream_t stream) {
+    if (p.apply_kind == 0) return vec ? launch_fused_v<false, true, kOutsSelectOnly>(p, stream)
+                                      : launch_fused_v<false, false, kOutsSelectOnly>(p, stream);
     if (!vec) return launch_fused_v<TRAIN, false, kOutsGeneric>(p, stream);
     const int outs = (p.apply_kind == 2) ? outs_of(p) : -2;
     if (outs == kOutsCodec) return launch_fused_v<TRAIN, true, kOutsCodec>(p, stream);
@@ -1133,7 +1174,8 @@ int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *f
 }
 
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units) {
-    if (n_per_unit <= kFusedMaxElems || units <= 0) return 256;  // fused path needs none; keep non-zero
+    if (units <= 0) return 256;
+    if (n_per_unit <= kFusedMaxElems) return ((static_cast<size_t>(units) * sizeof(float) + 255) / 256) * 256;  // thresholds
     return rounds_ws_bytes(units);
 }
 
@@ -1251,7 +1293,29 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
     p.mask = mask; p.y_hat = y_hat; p.lik = lik; p.idx = idx; p.symbols = symbols;
     p.thr_out = thr_out; p.rate = rate;
     p.apply_kind = 2;
-    if (n_per_unit <= kFusedMaxElems) return launch_fused(p, stream);
+    if (n_per_unit <= kFusedMaxElems) {
+        const bool sel = !thr_in && (q01_per_unit || unit_mode(q01) == kModeThreshold);
+        float *thr_buf = thr_out ? thr_out : ((ws && ws_bytes >= static_cast<size_t>(units) * sizeof(float)) ? static_cast<float *>(ws) : nullptr);
+        static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
+        const bool big = n_per_unit * units >= kTwoKernelMinElems;
+        // thresholds known: the tile-ordered apply kernel (global-order streaming, ~99 % of roofline)
+        if (two_kernel && thr_in && big) return launch_apply(p, stream);
+        // measured cross-over: per-unit fixed costs make the fused kernel better for small units
+        if (two_kernel && sel && thr_buf && big && n_per_unit >= kTwoKernelMinUnit) {
+            // large batch: lean select kernel (6 CTAs/SM) -> thresholds -> tile-ordered apply kernel.
+            // The apply kernel walks memory in global order and reaches ~99 % of the HBM roofline,
+            // which beats one-CTA-per-unit streaming (thousands of concurrent DRAM streams).
+            SliceParams ps = p;
+            ps.apply_kind = 0;
+            ps.thr_out = thr_buf;
+            rc = launch_fused(ps, stream);
+            if (rc != PIC_OK) return rc;
+            p.thr_in = thr_buf;
+            p.thr_out = nullptr;
+            return launch_apply(p, stream);
+        }
+        return launch_fused(p, stream);
+    }
     const bool needs_select = !thr_in && (q01_per_unit || unit_mode(q01) == kModeThreshold);
     if (needs_select) {
         if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;

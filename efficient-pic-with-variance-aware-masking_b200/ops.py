@@ -69,8 +69,6 @@ def _units_view(t: torch.Tensor, units: int) -> Tuple[int, int]:
 
 def _workspace(n_per_unit: int, units: int, device) -> Tuple[Optional[torch.Tensor], int]:
     nbytes = int(lib().pic_workspace_bytes(n_per_unit, units))
-    if n_per_unit <= fused_max_elems():
-        return None, 0
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     return ws, nbytes
 
