@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpic_latent.so")
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu")]
-_HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_select.cuh")] + [
+_HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh")] + [
     os.path.join(_ROOT, "include", "pic_latent.h")]
 
 PIC_OK = 0

@@ -543,6 +543,10 @@ slice_fused_kernel(const SliceParams p) {
     }
 }
 
+}  // namespace pic
+#include "pic_gselect.cuh"
+namespace pic {
+
 // ------------------------------------------------------------------------------------------
 // multi-CTA select rounds (large units; spatially tiled units)
 // ------------------------------------------------------------------------------------------
@@ -1050,6 +1054,33 @@ static int launch_apply(const SliceParams &p, cudaStream_t stream) {
     return PIC_OK;
 }
 
+// global sampled select (3 launches).  ws layout: [GsUnit x units][cand kCandMax x units][thr x units]
+static size_t gs_ws_bytes(int64_t units) {
+    return static_cast<size_t>(units) * (sizeof(GsUnit) + kCandMax * sizeof(uint32_t) + sizeof(float)) + 256;
+}
+static float *gs_thr_buffer(void *ws, int64_t units) {
+    unsigned char *b = static_cast<unsigned char *>(ws);
+    return reinterpret_cast<float *>(b + static_cast<size_t>(units) * (sizeof(GsUnit) + kCandMax * sizeof(uint32_t)));
+}
+static int select_sampled_global(const float *std, int64_t n, int64_t units, float q01, const float *q01_per_unit,
+                                 float *thr, float *a_out, float *b_out, void *ws, cudaStream_t stream) {
+    GsParams g{};
+    g.std = std; g.q01_per_unit = q01_per_unit; g.q01 = q01; g.n = n; g.units = units;
+    g.st = static_cast<GsUnit *>(ws);
+    g.cand = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(ws) + static_cast<size_t>(units) * sizeof(GsUnit));
+    g.thr = thr; g.a_out = a_out; g.b_out = b_out;
+    g.vec = ((n % 4 == 0) && aligned16(std)) ? 1 : 0;
+    const int tiles = static_cast<int>((n + kGsTile - 1) / kGsTile);
+    if (units * tiles > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
+    gs_pivot_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
+    if (n > kCandMax) {
+        if (g.vec) gs_sweep_kernel<true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+        else gs_sweep_kernel<false><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+        gs_finish_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
+    }
+    return launch_status();
+}
+
 // workspace layout of the multi-launch select: [state][hist x3 rounds][min_above]
 struct RoundsWs {
     SelectState *state;
@@ -1175,7 +1206,7 @@ int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *f
 
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units) {
     if (units <= 0) return 256;
-    if (n_per_unit <= kFusedMaxElems) return ((static_cast<size_t>(units) * sizeof(float) + 255) / 256) * 256;  // thresholds
+    if (n_per_unit <= kFusedMaxElems) return gs_ws_bytes(units);  // pivots, candidate buffers, thresholds
     return rounds_ws_bytes(units);
 }
 
@@ -1191,6 +1222,10 @@ int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, fl
     if (!aligned4(std)) return PIC_ERR_UNALIGNED;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_per_unit <= kFusedMaxElems) {
+        static const int gsel = [] { const char *e = getenv("PIC_GLOBAL_SELECT"); return e ? atoi(e) : 0; }();
+        if (gsel && ws && ws_bytes >= gs_ws_bytes(units) && n_per_unit * units >= kTwoKernelMinElems &&
+            n_per_unit >= kTwoKernelMinUnit)
+            return select_sampled_global(std, n_per_unit, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
         SliceParams p{};
         p.std = std; p.q01 = q01; p.q01_per_unit = q01_per_unit;
         p.n = n_per_unit; p.units = units;
@@ -1295,7 +1330,8 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
     p.apply_kind = 2;
     if (n_per_unit <= kFusedMaxElems) {
         const bool sel = !thr_in && (q01_per_unit || unit_mode(q01) == kModeThreshold);
-        float *thr_buf = thr_out ? thr_out : ((ws && ws_bytes >= static_cast<size_t>(units) * sizeof(float)) ? static_cast<float *>(ws) : nullptr);
+        const bool have_ws = ws && ws_bytes >= gs_ws_bytes(units);
+        float *thr_buf = thr_out ? thr_out : (have_ws ? gs_thr_buffer(ws, units) : nullptr);
         static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
         const bool big = n_per_unit * units >= kTwoKernelMinElems;
         // thresholds known: the tile-ordered apply kernel (global-order streaming, ~99 % of roofline)
@@ -1305,10 +1341,16 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
             // large batch: lean select kernel (6 CTAs/SM) -> thresholds -> tile-ordered apply kernel.
             // The apply kernel walks memory in global order and reaches ~99 % of the HBM roofline,
             // which beats one-CTA-per-unit streaming (thousands of concurrent DRAM streams).
-            SliceParams ps = p;
-            ps.apply_kind = 0;
-            ps.thr_out = thr_buf;
-            rc = launch_fused(ps, stream);
+            static const int gsel = [] { const char *e = getenv("PIC_GLOBAL_SELECT"); return e ? atoi(e) : 0; }();
+            if (gsel && have_ws) {
+                // global sampled select: std streamed tile by tile in global address order
+                rc = select_sampled_global(std, n_per_unit, units, q01, q01_per_unit, thr_buf, nullptr, nullptr, ws, stream);
+            } else {
+                SliceParams ps = p;
+                ps.apply_kind = 0;
+                ps.thr_out = thr_buf;
+                rc = launch_fused(ps, stream);
+            }
             if (rc != PIC_OK) return rc;
             p.thr_in = thr_buf;
             p.thr_out = nullptr;
