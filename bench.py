@@ -242,6 +242,11 @@ def run_cuda(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. the NCCL version
+    # banner) is sent to stderr, the JSON line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
@@ -450,7 +455,7 @@ def run_cuda(args, wl):
                                    else f"{world} rank(s), units sharded, no collective")},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
