@@ -264,8 +264,16 @@ def run_cuda(args, wl):
     table = pic_b200.get_scale_table().to(dev)
     q_slice = ops.q01_tensor(prs, dev)
     q_all = torch.cat([q_slice] * slices).contiguous()
+    import ctypes
+
+    def plan(n_, units_, needs_select=1):
+        k = ctypes.c_int(0)
+        kind = L.pic_slice_forward_plan(n_, units_, needs_select, ctypes.byref(k))
+        return kind, k.value
+
     fused = n <= int(L.pic_fused_max_elems())
     launches = [0]
+    PLAN_KERNEL = {0: "slice_fused_kernel", 1: "slice_apply_kernel", 2: "slice_apply_kernel"}
     main_kernel = "slice_fused_kernel"
 
     if name == "tile8192":
@@ -297,10 +305,13 @@ def run_cuda(args, wl):
         want = ("mask", "y_hat", "lik")
         outs = {k: torch.empty((units, n), dtype=torch.float32, device=dev) for k in want}
 
+        fwd_kind, fwd_k = plan(n, units)
+        main_kernel = PLAN_KERNEL[fwd_kind]
+
         def step():
             ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)
             ops.slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, outs["mask"], noise)
-            launches[0] = 2
+            launches[0] = fwd_k + 1
         elems_per_rank = units * n
         total_elems = elems_per_rank * world
     else:
@@ -312,16 +323,19 @@ def run_cuda(args, wl):
         def view(t, s):
             return t[s * per_slice:(s + 1) * per_slice]
 
+        step_kind, step_k = plan(n, units) if args.launch == "per_step" else plan(n, per_slice)
+        main_kernel = PLAN_KERNEL[step_kind]
+
         def step():
             if args.launch == "per_step":
                 ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
-                launches[0] = 1 if fused else 9
+                launches[0] = step_k
             else:
                 for s in range(slices):
                     o = {k: view(v, s) for k, v in outs.items()}
                     ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice,
                                       table, want=want, out=o)
-                launches[0] = slices * (1 if fused else 9)
+                launches[0] = slices * step_k
         elems_per_rank = units * n
         total_elems = elems_per_rank * world
 
@@ -401,8 +415,30 @@ def run_cuda(args, wl):
     hbm, which = peaks()
     roof = None
     if rank == 0 or world > 1:
-        if name == "kodak_sweep" and args.launch == "per_step" and fused:
+        other = None
+        if name == "kodak_sweep" and args.launch == "per_step" and step_kind == 0:
             kern_ms, per_launch_elems = ms_per_step, units * n       # the step IS one launch of the kernel
+        elif name == "kodak_sweep" and args.launch == "per_step":
+            # plan 1: select kernel + tile-ordered apply kernel.  Time the dominant (apply) kernel alone
+            # with the thresholds given, and the select kernel alone, with CUDA events on this stream.
+            def ev_time(fn, reps=20):
+                fn()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    fn()
+                a1.record()
+                torch.cuda.synchronize()
+                return a0.elapsed_time(a1) / reps
+            thr0 = ops.select_threshold(std, units, q_all)
+            kern_ms = ev_time(lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr0,
+                                                        want=want, out=outs))
+            sel_ms = ev_time(lambda: ops.select_threshold(std, units, q_all))
+            per_launch_elems = units * n
+            other = {"select_kernel": "slice_fused_kernel<select-only>", "select_ms": sel_ms,
+                     "select_GBps_of_std": units * n * 4 / (sel_ms * 1e-3) / 1e9,
+                     "apply_share_of_step": kern_ms / ms_per_step}
         else:
             reps = 10
             if name == "first_train":
@@ -437,7 +473,8 @@ def run_cuda(args, wl):
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic, "peak_source": which, "kernel": main_kernel,
                 "algorithmic_bytes_per_elem": kbytes, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "launch_ms": kern_ms}
+                "launch_ms": kern_ms, "other_kernels": other,
+                "whole_step_frac": (elems_per_rank * wl["bytes_per_elem"] / (ms_per_step * 1e-3) / 1e9) / hbm}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

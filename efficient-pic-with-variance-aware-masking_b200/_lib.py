@@ -40,6 +40,7 @@ SIGNATURES = {
     "pic_last_cuda_error": (C.c_int, []),
     "pic_fused_max_elems": (_i64, []),
     "pic_debug_select_counters": (C.c_int, [_vp, _vp]),
+    "pic_slice_forward_plan": (C.c_int, [_i64, _i64, _i32, _vp]),
     "pic_workspace_bytes": (_sz, [_i64, _i64]),
     "pic_select_threshold": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pic_select_state_bytes": (_sz, [_i64]),

@@ -190,6 +190,9 @@ __device__ __forceinline__ int scale_index_fast(float sc, const IndexCtx &c) {
     return g + (!(sc <= c.tbl[g]) ? 1 : 0);   // !(<=) is also true for NaN -> len-1, like the reference
 }
 
+__device__ __forceinline__ void likelihood_pair(float v0, float v1, float sc0, float sc1, float lik_bound,
+                                                float &lik0, float &lik1);
+
 // One pair of elements of a progressive slice (same arithmetic as apply_one in pic_latent.cu).
 // s, yt, yb, mu, nz: the two elements' inputs.  want_lik / want_idx are warp-uniform.
 template <bool TRAIN>
@@ -235,7 +238,14 @@ __device__ __forceinline__ void apply_pair(const float s[2], const float yt[2], 
         out0 = rintf(ym0);
         out1 = rintf(ym1);
     }
-    const f2 v = pk(fabsf(out0), fabsf(out1));
+    likelihood_pair(fabsf(out0), fabsf(out1), sc0, sc1, lik_bound, o.lik[0], o.lik[1]);
+}
+
+// lik = max(Phi((.5 - v)/sc) - Phi((-.5 - v)/sc), lik_bound) for two elements (v = |x| >= 0,
+// sc = lower-bounded scale), entropy_models.py:620-635, 649-650.
+__device__ __forceinline__ void likelihood_pair(float v0, float v1, float sc0, float sc1, float lik_bound,
+                                                float &lik0, float &lik1) {
+    const f2 v = pk(v0, v1);
     const f2 sc = pk(sc0, sc1);
     // -1/sc: MUFU + Newton
     const f2 nrc0 = pk(rcp_approx(-sc0), rcp_approx(-sc1));
@@ -262,8 +272,8 @@ __device__ __forceinline__ void apply_pair(const float s[2], const float yt[2], 
     const f2 up = pk((xu0 < 0.0f) ? om0 : hu0, (xu1 < 0.0f) ? om1 : hu1);
     float l0, l1;
     unpk(sub2(up, lo), l0, l1);
-    o.lik[0] = (lik_bound > 0.0f) ? max_nan(l0, lik_bound) : l0;
-    o.lik[1] = (lik_bound > 0.0f) ? max_nan(l1, lik_bound) : l1;
+    lik0 = (lik_bound > 0.0f) ? max_nan(l0, lik_bound) : l0;
+    lik1 = (lik_bound > 0.0f) ? max_nan(l1, lik_bound) : l1;
 }
 
 }  // namespace pic

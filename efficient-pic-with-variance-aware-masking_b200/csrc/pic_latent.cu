@@ -323,9 +323,10 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         const int nvec = n >> 2, S4 = S >> 2;
         const int stride = nvec / S4;  // >= 1 because n > kCandMax >= S
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
+        const uint64_t pol_keep = policy_evict_last();   // the sweep re-reads these lines within microseconds
         for (int i = tid; i < S4; i += THREADS) {
             const uint32_t jit = ((static_cast<uint32_t>(i) * 0x9E3779B1u) >> 12) % static_cast<uint32_t>(stride);
-            const float4 v = __ldg(s4 + static_cast<size_t>(i) * stride + jit);
+            const float4 v = ld_hint(s4 + static_cast<size_t>(i) * stride + jit, pol_keep);
             reinterpret_cast<uint4 *>(cand)[i] =
                 make_uint4(float_to_key(v.x), float_to_key(v.y), float_to_key(v.z), float_to_key(v.w));
         }
@@ -799,13 +800,10 @@ __global__ void __launch_bounds__(256) gaussian_forward_kernel(const float *inpu
                                                                const float *means, const float *noise,
                                                                int64_t n, float scale_bound, float lik_bound,
                                                                float *outputs, float *lik) {
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const float x = inputs[j];
-        const float mu = means ? means[j] : 0.0f;
-        float out;
+    const float lb = (KIND == 2) ? 0.0f : lik_bound;
+    auto quant = [&](float x, float mu, float nz, float &out, float &value) {
         if (KIND == 1) {
-            out = __fadd_rn(x, noise[j]);
+            out = __fadd_rn(x, nz);
         } else if (KIND == 0) {
             float t = means ? __fsub_rn(x, mu) : x;
             t = rintf(t);
@@ -813,9 +811,35 @@ __global__ void __launch_bounds__(256) gaussian_forward_kernel(const float *inpu
         } else {
             out = x;
         }
-        const float value = means ? __fsub_rn(out, mu) : out;
-        if (outputs) outputs[j] = out;
-        if (lik) lik[j] = likelihood(value, scales[j], scale_bound, (KIND == 2) ? 0.0f : lik_bound);
+        value = means ? __fsub_rn(out, mu) : out;
+    };
+    // two elements per iteration through the packed-f32 likelihood (pic_fast.cuh)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t pairs = n >> 1;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < pairs; j += stride) {
+        const int64_t i0 = 2 * j, i1 = i0 + 1;
+        float o0, o1, v0, v1;
+        quant(inputs[i0], means ? means[i0] : 0.0f, (KIND == 1) ? noise[i0] : 0.0f, o0, v0);
+        quant(inputs[i1], means ? means[i1] : 0.0f, (KIND == 1) ? noise[i1] : 0.0f, o1, v1);
+        if (outputs) { outputs[i0] = o0; outputs[i1] = o1; }
+        if (lik) {
+            float l0, l1;
+            likelihood_pair(fabsf(v0), fabsf(v1), max_nan(scales[i0], scale_bound), max_nan(scales[i1], scale_bound),
+                            lb, l0, l1);
+            lik[i0] = l0;
+            lik[i1] = l1;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i0 = n - 1;
+        float o0, v0, l0, l1;
+        quant(inputs[i0], means ? means[i0] : 0.0f, (KIND == 1) ? noise[i0] : 0.0f, o0, v0);
+        if (outputs) outputs[i0] = o0;
+        if (lik) {
+            const float sc = max_nan(scales[i0], scale_bound);
+            likelihood_pair(fabsf(v0), fabsf(v0), sc, sc, lb, l0, l1);
+            lik[i0] = l0;
+        }
     }
 }
 
@@ -1196,6 +1220,23 @@ const char *pic_error_string(int code) {
 int pic_last_cuda_error(void) { return g_last_cuda_error; }
 
 int64_t pic_fused_max_elems(void) { return kFusedMaxElems; }
+
+int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, int *n_kernels) {
+    if (n_per_unit <= 0 || units <= 0 || !n_kernels) return PIC_ERR_INVALID_ARGUMENT;
+    const bool big = n_per_unit * units >= kTwoKernelMinElems;
+    static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
+    static const int gsel = [] { const char *e = getenv("PIC_GLOBAL_SELECT"); return e ? atoi(e) : 0; }();
+    if (n_per_unit > kFusedMaxElems) {
+        *n_kernels = needs_select ? 9 : 1;   // begin + 3 x (hist, advance) + finish + apply
+        return 2;
+    }
+    if (two_kernel && big && (!needs_select || n_per_unit >= kTwoKernelMinUnit)) {
+        *n_kernels = needs_select ? (gsel ? 4 : 2) : 1;   // select kernel(s) + tile-ordered apply
+        return 1;
+    }
+    *n_kernels = 1;                              // single fused kernel
+    return 0;
+}
 
 int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback) {
     PIC_CUDA_CHECK(cudaDeviceSynchronize());

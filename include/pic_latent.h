@@ -66,6 +66,11 @@ int pic_last_cuda_error(void); /* cudaError_t of the last failing runtime call o
  * shared memory between select and apply); larger units take the multi-launch path. */
 int64_t pic_fused_max_elems(void);
 
+/* Launch plan of pic_slice_forward for a problem size: returns 0 (single fused kernel), 1 (select
+ * kernel + tile-ordered apply kernel) or 2 (multi-launch radix rounds + apply kernel) and stores the
+ * number of kernel launches in *n_kernels.  needs_select = 0 when thresholds are supplied. */
+int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, int *n_kernels);
+
 /* Diagnostics (synchronises the device): number of units served by the sampled-pivot select and
  * number that fell back to the full histogram select, since the library was loaded. */
 int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback);

@@ -11,7 +11,10 @@ rep = sys.argv[1]
 elems = float(sys.argv[2]) if len(sys.argv) > 2 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+vals = rows[2 + which]
+print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?", " (result", which, "of", len(rows) - 2, ")")
 keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -37,6 +40,10 @@ if elems and "smsp__inst_executed.sum" in d:
     inst = float(d["smsp__inst_executed.sum"][0].replace(",", ""))
     print(f"lane-instructions per element: {inst * 32 / elems:.1f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+# the source page concatenates one block per profiled kernel: keep block `which`
+blocks = src.split('"Kernel Name"')
+if len(blocks) > 1:
+    src = '"Kernel Name"' + blocks[1 + min(which, len(blocks) - 2)]
 rows = list(csv.reader(io.StringIO(src)))
 hdr = None
 agg = collections.OrderedDict()
