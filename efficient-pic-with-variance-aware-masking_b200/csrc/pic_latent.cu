@@ -1223,14 +1223,13 @@ int64_t pic_fused_max_elems(void) { return kFusedMaxElems; }
 
 int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, int *n_kernels) {
     if (n_per_unit <= 0 || units <= 0 || !n_kernels) return PIC_ERR_INVALID_ARGUMENT;
-    const bool big = n_per_unit * units >= kTwoKernelMinElems;
     static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
     static const int gsel = [] { const char *e = getenv("PIC_GLOBAL_SELECT"); return e ? atoi(e) : 0; }();
     if (n_per_unit > kFusedMaxElems) {
         *n_kernels = needs_select ? 9 : 1;   // begin + 3 x (hist, advance) + finish + apply
         return 2;
     }
-    if (two_kernel && big && (!needs_select || n_per_unit >= kTwoKernelMinUnit)) {
+    if (two_kernel && (!needs_select || n_per_unit >= kTwoKernelMinUnit)) {
         *n_kernels = needs_select ? (gsel ? 4 : 2) : 1;   // select kernel(s) + tile-ordered apply
         return 1;
     }
@@ -1374,11 +1373,12 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
         const bool have_ws = ws && ws_bytes >= gs_ws_bytes(units);
         float *thr_buf = thr_out ? thr_out : (have_ws ? gs_thr_buffer(ws, units) : nullptr);
         static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
-        const bool big = n_per_unit * units >= kTwoKernelMinElems;
         // thresholds known: the tile-ordered apply kernel (global-order streaming, ~99 % of roofline)
-        if (two_kernel && thr_in && big) return launch_apply(p, stream);
-        // measured cross-over: per-unit fixed costs make the fused kernel better for small units
-        if (two_kernel && sel && thr_buf && big && n_per_unit >= kTwoKernelMinUnit) {
+        if (two_kernel && thr_in) return launch_apply(p, stream);
+        // measured cross-over (scripts/small_batch.py, phase_bench.py): for units of >= 32768 elements the
+        // select kernel + tile-ordered apply wins at every batch size (few units: the apply spreads over
+        // tiles; many units: global-order streaming); below that per-unit fixed costs favour one fused launch
+        if (two_kernel && sel && thr_buf && n_per_unit >= kTwoKernelMinUnit) {
             // large batch: lean select kernel (6 CTAs/SM) -> thresholds -> tile-ordered apply kernel.
             // The apply kernel walks memory in global order and reaches ~99 % of the HBM roofline,
             // which beats one-CTA-per-unit streaming (thousands of concurrent DRAM streams).
