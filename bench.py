@@ -373,7 +373,7 @@ def run_cuda(args, wl):
     # ---------------- end-to-end: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ---
     e2e = None
     if not args.no_e2e and name == "kodak_sweep":
-        chunk = max(1, min(per_slice, (48 << 20) // (n * 4)))
+        chunk = args.e2e_chunk if args.e2e_chunk > 0 else max(1, min(per_slice, (48 << 20) // (n * 4)))
         host_in = [t.cpu().pin_memory() for t in (y_top, y_base, mu, std)]
         q_host = q_all.cpu().pin_memory()
         host_out = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32).pin_memory()
@@ -509,6 +509,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="units per pipeline chunk of the host-buffer path (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

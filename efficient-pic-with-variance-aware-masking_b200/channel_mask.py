@@ -99,6 +99,14 @@ class ChannelMask(nn.Module):
         else:
             raise NotImplementedError()
 
+    # ------------------------------------------------------------------ REM attention mask
+    def attention_mask(self, scale, pr, training=False, mu_std=False, mask_pol="point-based-std"):
+        """models/rem_pic.py:181-195 (apply_latent_enhancement): the `star_mask` at quality `pr` on the
+        pre-REM scale, rounded, duplicated on the channel axis when the REM refines (mu, std) jointly.
+        (The reference also computes a `bar_mask` at `quality_bar` and discards it; not reproduced.)"""
+        m = self.apply_noise(self.forward(scale, pr=pr, mask_pol=mask_pol), training)
+        return torch.cat([m, m], dim=1) if mu_std else m
+
     # ------------------------------------------------------------------ extensions (not in the reference)
     def forward_multi(self, scale, prs):
         """One quality level per image/unit: `prs` is a sequence of len(scale) qualities or a

@@ -433,3 +433,60 @@ def test_tiled_select_single_process(pic, dev):
     assert np.array_equal(N(thr), rthr)
     for be in bes[1:]:
         assert torch.equal(be.finish(mins), thr)
+
+
+def test_rem_attention_mask_and_rate(pic, dev):
+    """REM variant (BASELINE config[3]): duplicated [B,64,h,w] attention mask (rem_pic.py:181-195) and the
+    rate reduction of training/loss.py:45-60."""
+    rng = np.random.default_rng(8)
+    std = trained_like(rng, (2, 32, 8, 8))[3]
+    masking = pic.ChannelMask("point-based-std")
+    s = T(std, dev)
+    att = masking.attention_mask(s, 0.75, training=False, mu_std=True)
+    ref, _ = po.channel_mask(std.reshape(2, -1), 0.75)
+    assert att.shape == (2, 64, 8, 8)
+    assert np.array_equal(N(att[:, :32]), ref.reshape(2, 32, 8, 8)) and torch.equal(att[:, :32], att[:, 32:])
+    lik = torch.rand(3, 32, 16, 16, device=dev) * 0.9 + 0.05
+    bpp = pic.rate_bpp(lik, num_pixels=3 * 256 * 256)
+    want = float(torch.log(lik.double()).sum() / (-np.log(2) * 3 * 256 * 256))
+    assert abs(float(bpp) - want) <= 1e-6 * abs(want)
+
+
+@pytest.mark.gpu
+def test_global_select_variant_subprocess():
+    """The optional three-kernel global sampled select (PIC_GLOBAL_SELECT=1) is read from the environment at
+    first use, so it is exercised in a fresh process: thresholds and masks must equal the oracle's."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/oracle'); sys.path.insert(0, %r + '/tests')
+import pic_b200, pic_oracle as po
+from pic_b200 import ops
+from _common import trained_like, scale_table
+dev = torch.device('cuda:0')
+rng = np.random.default_rng(4)
+for units, n in ((130, 49152), (40, 131072), (200, 32768)):
+    y_top, y_base, mu, std = trained_like(rng, (units, n))
+    std[:, ::9] = np.round(std[:, ::9] * 8) / 8
+    prs = [[0.5, 1, 5, 9.9999, 10, 0, 2.5][u %% 7] for u in range(units)]
+    q = ops.q01_tensor(prs, dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    out = ops.slice_forward(t(y_top), t(y_base), t(mu), t(std), units, q, t(scale_table()), want=('mask', 'thr', 'idx'))
+    ref = po.slice_forward(y_top, y_base, mu, std, prs, scale_table(), want=('mask', 'thr', 'idx'))
+    assert np.array_equal(out['thr'].cpu().numpy(), ref['thr']), (units, n)
+    assert np.array_equal(out['mask'].cpu().numpy(), ref['mask'])
+    assert np.array_equal(out['idx'].cpu().numpy(), ref['idx'])
+    thr = ops.select_threshold(t(std), units, q)
+    assert np.array_equal(thr.cpu().numpy(), ref['thr'])
+import ctypes
+k = ctypes.c_int(0)
+assert pic_b200.lib().pic_slice_forward_plan(49152, 130, 1, ctypes.byref(k)) == 1 and k.value == 4
+print('global-select ok')
+""" % (root, root, root)
+    env = dict(os.environ, PIC_GLOBAL_SELECT="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "global-select ok" in res.stdout, res.stdout + res.stderr
