@@ -43,6 +43,8 @@ SIGNATURES = {
     "pic_slice_forward_plan": (C.c_int, [_i64, _i64, _i32, _vp]),
     "pic_workspace_bytes": (_sz, [_i64, _i64]),
     "pic_select_threshold": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pic_select_threshold_multi": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "pic_level_map": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "pic_select_state_bytes": (_sz, [_i64]),
     "pic_hist_words": (_i64, []),
     "pic_select_begin": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),

@@ -56,6 +56,19 @@ class ChannelMask(nn.Module):
         mask = ops.channel_mask(stacked, stacked.shape[0], q01)
         return mask.reshape(len(blocks) * bs, ch, w, h)
 
+    def ProgLevels(self, scale, q_list):
+        """All progressive levels at once (test/functions_encode.py:176-190: two ProgMask calls per level
+        on the same scale list).  `scale`: list of per-slice blocks [1, ch, w, h]; `q_list`: increasing
+        qualities.  Returns (level, thr): level [len(scale), ch, w, h] int32 with the first level that keeps
+        each element (len(q_list) if none) -- ProgMask(q_l) - ProgMask(q_{l-1}) == (level == l), with
+        q_{-1} = 0 -- and the thresholds thr [len(scale), len(q_list)]."""
+        blocks = [b if b.is_contiguous() else b.contiguous() for b in scale]
+        bs, ch, w, h = blocks[0].shape
+        stacked = torch.cat([b.reshape(bs, ch * w * h) for b in blocks], dim=0)
+        thr = ops.select_threshold_multi(stacked, stacked.shape[0], list(q_list))
+        level = ops.level_map(stacked, thr, stacked.shape[0])
+        return level.reshape(len(blocks) * bs, ch, w, h), thr
+
     def delta_mask(self, scale, pr_bar, pr):
         raise NotImplementedError("delta_mask is dead code in the reference (chained tensor comparison raises)")
 

@@ -86,6 +86,7 @@ struct SliceParams {
     double *rate;
     int apply_kind;  // 0: select only, 1: mask only, 2: full slice
     int use_stage;   // dynamic shared memory holds the cp.async stage buffer
+    int repeat;      // select-only: `repeat` consecutive (virtual) units share one std block (multi-quality select)
 };
 
 // diagnostics: units whose sampled bracket missed (counted since library load)
@@ -488,7 +489,7 @@ slice_fused_kernel(const SliceParams p) {
     if (OUTS != kOutsSelectOnly) ic = index_ctx_setup(p, sm.index);
 
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const int64_t off = u * p.n;
+        const int64_t off = ((OUTS == kOutsSelectOnly && p.repeat > 1) ? u / p.repeat : u) * p.n;
         const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
         const int mode = unit_mode(q);
         float thr = (mode == kModeOnes) ? -INFINITY : INFINITY;
@@ -933,6 +934,38 @@ __global__ void __launch_bounds__(256) mask_from_threshold_kernel(const float *s
     }
 }
 
+// Progressive level map (test/functions_encode.py:176-190, functions_decode.py:186-200): for thresholds
+// thr[u][0..Q) of increasing quality, level[e] = first l with std[e] >= thr[u][l], or Q when no level keeps
+// the element.  The delta mask of level l (ProgMask(q_l) - ProgMask(q_{l-1})) is exactly (level == l).
+__global__ void __launch_bounds__(256) level_map_kernel(const float *std, const float *thr, int64_t n_per_unit,
+                                                        int64_t total, int levels, int32_t *level) {
+    extern __shared__ float sthr[];   // levels floats of the CTA's unit (grid-stride loops stay inside one unit)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t cached_u = -1;
+    for (int64_t j0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; j0 < total; j0 += stride) {
+        const int64_t u = j0 / n_per_unit;                       // unit of the CTA's first element
+        if (u != cached_u) {
+            __syncthreads();
+            for (int l = threadIdx.x; l < levels; l += blockDim.x) sthr[l] = thr[u * levels + l];
+            __syncthreads();
+            cached_u = u;
+        }
+        const int64_t j = j0 + threadIdx.x;
+        if (j >= total) continue;
+        const float s = std[j];
+        const int64_t uj = j / n_per_unit;
+        int lv = levels;
+        if (uj == u) {
+            for (int l = 0; l < levels; ++l)
+                if (s >= sthr[l]) { lv = l; break; }
+        } else {                                                  // CTA straddles a unit boundary
+            for (int l = 0; l < levels; ++l)
+                if (s >= thr[uj * levels + l]) { lv = l; break; }
+        }
+        level[j] = lv;
+    }
+}
+
 // per-unit sum ln(x): grid (chunks, units), atomics in f64 (out pre-zeroed)
 __global__ void __launch_bounds__(256) log_sum_kernel(const float *x, int64_t n_per_unit, double *out) {
     __shared__ double red[8];
@@ -1275,6 +1308,34 @@ int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, fl
     }
     if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
     return select_rounds(std, n_per_unit, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
+}
+
+int pic_select_threshold_multi(const float *std, int64_t n_per_unit, int64_t units, const float *q01_levels,
+                               int levels, float *thr_out, pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!std || !q01_levels || !thr_out || levels < 1) return PIC_ERR_INVALID_ARGUMENT;
+    if (n_per_unit > kFusedMaxElems) return PIC_ERR_TOO_LARGE;   // larger units: call pic_select_threshold per level
+    if (!aligned4(std)) return PIC_ERR_UNALIGNED;
+    SliceParams p{};
+    p.std = std;
+    p.q01_per_unit = q01_levels;          // [units * levels], level-minor
+    p.n = n_per_unit;
+    p.units = units * levels;             // virtual units: `levels` consecutive ones share one std block
+    p.repeat = levels;
+    p.thr_out = thr_out;
+    p.apply_kind = 0;
+    return launch_fused(p, static_cast<cudaStream_t>(stream_));
+}
+
+int pic_level_map(const float *std, const float *thr, int64_t n_per_unit, int64_t units, int levels,
+                  int32_t *level, pic_stream_t stream_) {
+    if (n_per_unit <= 0 || units <= 0 || levels < 1 || levels > 4096 || !std || !thr || !level)
+        return PIC_ERR_INVALID_ARGUMENT;
+    const int64_t total = n_per_unit * units;
+    level_map_kernel<<<elementwise_grid(total, 1), 256, levels * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(
+        std, thr, n_per_unit, total, levels, level);
+    return launch_status();
 }
 
 int pic_select_begin(void *state, int64_t n_total, int64_t units, float q01, const float *q01_per_unit,

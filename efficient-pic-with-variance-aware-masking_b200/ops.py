@@ -121,6 +121,28 @@ def channel_mask(std: torch.Tensor, units: int, q01, want_thr: bool = False):
     return (mask, thr) if want_thr else mask
 
 
+def select_threshold_multi(std: torch.Tensor, units: int, prs: Sequence[Number]) -> torch.Tensor:
+    """Thresholds of every unit at every quality of `prs` in one launch. Returns thr [units, len(prs)]."""
+    std = _require(std, "std")
+    units, n = _units_view(std, units)
+    levels = len(prs)
+    q = q01_tensor(list(prs) * units, std.device)          # [units, levels], level-minor
+    thr = torch.empty((units, levels), dtype=torch.float32, device=std.device)
+    check(lib().pic_select_threshold_multi(_ptr(std), n, units, _ptr(q), levels, _ptr(thr), _stream()),
+          "pic_select_threshold_multi")
+    return thr
+
+
+def level_map(std: torch.Tensor, thr: torch.Tensor, units: int) -> torch.Tensor:
+    """level[e] = first l with std[e] >= thr[u, l] (or L): delta mask of level l == (level == l)."""
+    std, thr = _require(std, "std"), _require(thr, "thr")
+    units, n = _units_view(std, units)
+    levels = thr.numel() // units
+    out = torch.empty(std.shape, dtype=torch.int32, device=std.device)
+    check(lib().pic_level_map(_ptr(std), _ptr(thr), n, units, levels, _ptr(out), _stream()), "pic_level_map")
+    return out
+
+
 def mask_from_threshold(std: torch.Tensor, thr: torch.Tensor, units: int) -> torch.Tensor:
     std, thr = _require(std, "std"), _require(thr, "thr")
     units, n = _units_view(std, units)

@@ -90,6 +90,21 @@ int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, fl
                          void *ws, size_t ws_bytes, pic_stream_t stream);
 
 /*
+ * (1a) Multi-quality form of (1) for progressive level packing (test/functions_encode.py:176-190,
+ * functions_decode.py:186-200, which call ProgMask twice per level on the same scale list):
+ * q01_levels is a device array [units][levels] (level-minor); thr_out receives [units][levels].
+ * All levels of a unit are selected in one launch from the same std block (n_per_unit <=
+ * pic_fused_max_elems()).  pic_level_map then yields, per element, the first level l with
+ * std >= thr[u][l] (or `levels`): the delta mask ProgMask(q_l) - ProgMask(q_{l-1}) of nested
+ * quality levels is exactly (level == l).
+ */
+int pic_select_threshold_multi(const float *std, int64_t n_per_unit, int64_t units,
+                               const float *q01_levels, int levels, float *thr_out,
+                               pic_stream_t stream);
+int pic_level_map(const float *std, const float *thr, int64_t n_per_unit, int64_t units, int levels,
+                  int32_t *level, pic_stream_t stream);
+
+/*
  * (1b) Split form of (1) for spatially tiled units (one image sharded over several GPUs,
  * SURVEY 8e).  Radix rounds r = 0,1,2 (11/11/10 key bits).  Per round every rank calls
  * pic_hist_round() on its local tile, all-reduces `hist` (uint32 sum, pic_hist_words() words

@@ -490,3 +490,31 @@ print('global-select ok')
     env = dict(os.environ, PIC_GLOBAL_SELECT="1")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "global-select ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.gpu
+def test_progressive_levels(pic, dev):
+    """SURVEY 8(f) row 1 -- progressive multi-level packing (test/functions_encode.py:176-190): the delta mask of
+    level l, ProgMask(q_l) - ProgMask(q_{l-1}), equals (level == l) from ONE multi-quality select + level map."""
+    rng = np.random.default_rng(17)
+    blocks = [trained_like(rng, (1, 32, 8, 12))[3] for _ in range(10)]
+    blocks[3][0, ::2] = np.round(blocks[3][0, ::2] * 8) / 8          # ties
+    q_list = [0.5, 1, 2.5, 5, 7.5, 10]                               # last level: everything that is left
+    masking = pic.ChannelMask("point-based-std")
+    level, thr = masking.ProgLevels([T(b, dev) for b in blocks], q_list)
+    assert level.shape == (10, 32, 8, 12) and level.dtype == torch.int32 and thr.shape == (10, len(q_list))
+    flat = np.stack(blocks).reshape(10, -1)
+    prev = np.zeros_like(flat)
+    lv = N(level).reshape(10, -1)
+    for l, q in enumerate(q_list):
+        cur, rthr = po.channel_mask(flat, q)                         # == ProgMask(scale_slices, q)
+        delta = cur - prev
+        assert np.array_equal(delta, (lv == l).astype(np.float32)), (l, q)
+        if 0 < q < 10:
+            assert np.array_equal(N(thr)[:, l], rthr), (l, q)
+        prev = cur
+    assert (lv == len(q_list)).sum() == 0                            # q = 10 keeps every element
+    # the per-level symbol / index streams of the reference are then plain selections
+    sym = torch.randint(-5, 6, level.shape, device=dev, dtype=torch.int32)
+    lvl2 = torch.where(level == 2, sym, torch.zeros_like(sym))
+    assert torch.equal(lvl2, sym * T(((lv == 2).astype(np.int32)).reshape(level.shape), dev))
