@@ -13,6 +13,8 @@ Workloads (--workload):
       every rank runs a full replica on its own data, no collective on the data path.
   first_train (config[2]): [256,32,16,16] x 10 slices, random quality per image, training-mode forward
       (noise) + fused backward.  Weak scaling, no collective.
+  rem_latent (config[3]): REM variant of the path at the first_train shape: 3 threshold selections per slice
+      (pre-REM attention mask duplicated to [B,64,h,w], checkpoint pass at q = 0.75, post-REM block mask) + slice.
   tile8192 (config[4]): one 8192x8192 image, 10 slices of n=8388608, each rank holds a row band; the
       per-slice threshold comes from NCCL all-reduced radix histograms.  Strong scaling.
 Inputs of one step are far larger than the 126 MB L2 (kodak_sweep: 794 MB), so consecutive steps stream
@@ -45,6 +47,11 @@ WORKLOADS = {
                         desc="256 crops of 256x256, 10 slices, random q per image, training forward + backward",
                         bytes_per_elem=32 + 48,  # fwd: 5 in (incl. noise) + 3 out; bwd: 8 in + 4 out
                         ),
+    "rem_latent": dict(n=32 * 16 * 16, slices=10, prs=None, batch=256, scaling="weak",
+                       desc="REM variant (mu_std): per slice 3 threshold selections (pre-REM star mask duplicated to "
+                            "[B,64,h,w], checkpoint pass at q=0.75, post-REM block mask) + the fused slice forward",
+                       bytes_per_elem=4 + 8 + 4 + 32,  # star select + duplicated mask write, checkpoint select, slice fwd
+                       ),
     "tile8192": dict(n=32 * 512 * 512, slices=10, prs=[1.0], scaling="strong",
                      desc="single 8192x8192 image, 10 slices, q=1, row bands over the ranks, NCCL histogram all-reduce",
                      bytes_per_elem=36,  # std read by the select rounds (>=1 pass from HBM) + the 32 of the apply
@@ -314,6 +321,26 @@ def run_cuda(args, wl):
             launches[0] = fwd_k + 1
         elems_per_rank = units * n
         total_elems = elems_per_rank * world
+    elif name == "rem_latent":
+        # models/rem_pic.py:181-195 (star mask on the pre-REM scale, duplicated for mu_std), 121-132 (checkpoint
+        # representation at quality_ref = 0.75 -> a second select), 382-391 (block mask on the refined scale + slice)
+        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
+        _, _, _, std_pre = make_device_inputs(torch, n, units, seed + 17, dev)
+        want = ("mask", "y_hat", "lik")
+        outs = {k: torch.empty((units, n), dtype=torch.float32, device=dev) for k in want}
+        att = torch.empty((units, 2, n), dtype=torch.float32, device=dev)
+        fwd_kind, fwd_k = plan(n, units)
+        main_kernel = PLAN_KERNEL[fwd_kind]
+
+        def step():
+            star = ops.channel_mask(std_pre, units, q_all)               # pre-REM attention mask
+            att[:, 0].copy_(star)
+            att[:, 1].copy_(star)                                        # cat([m, m], 1) for mu_std
+            ops.select_threshold(std_pre, units, ops.pr_to_q01(0.75))    # checkpoint pass threshold
+            ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs)
+            launches[0] = 2 + fwd_k                                      # ours; the two copies are torch's
+        elems_per_rank = units * n
+        total_elems = elems_per_rank * world
     else:
         y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
         want = ("mask", "y_hat", "lik", "idx")
@@ -444,6 +471,9 @@ def run_cuda(args, wl):
             if name == "first_train":
                 fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)  # noqa: E731
                 per_launch_elems = units * n
+            elif name == "rem_latent":
+                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs)  # noqa: E731
+                per_launch_elems = units * n
             elif name == "tile8192":
                 thr0 = ops.select_threshold(std, units, q_all) if world == 1 else pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
                 fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr0, want=want, out=outs)  # noqa: E731
@@ -460,7 +490,7 @@ def run_cuda(args, wl):
             k1.record()
             torch.cuda.synchronize()
             kern_ms = k0.elapsed_time(k1) / reps
-        kbytes = {"first_train": 32, "tile8192": 32}.get(name, wl["bytes_per_elem"])
+        kbytes = {"first_train": 32, "tile8192": 32, "rem_latent": 28}.get(name, wl["bytes_per_elem"])
         bytes_per_launch = per_launch_elems * kbytes
         achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
         traffic = None
