@@ -113,6 +113,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// classification helpers of the select sweep (instruction-count critical: the sweep is issue-bound)
+// 1.0f if a < b else 0.0f (one FSET)
+__device__ __forceinline__ float fset_lt(float a, float b) {
+    float d;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+// hits |= BIT if lo <= x <= hi (two FSETP + one predicated OR); false for NaN
+template <uint32_t BIT>
+__device__ __forceinline__ void or_if_in_range(uint32_t &hits, float x, float lo, float hi) {
+    asm("{ .reg .pred p, q; setp.ge.f32 p, %1, %2; setp.le.and.f32 q, %1, %3, p; @q or.b32 %0, %0, %4; }"
+        : "+r"(hits) : "f"(x), "f"(lo), "f"(hi), "n"(BIT));
+}
+
 // NaN-propagating min / max (torch.max(x, bound) semantics of LowerBound)
 __device__ __forceinline__ float max_nan(float a, float b) {
     float r;

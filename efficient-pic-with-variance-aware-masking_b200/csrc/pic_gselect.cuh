@@ -140,17 +140,21 @@ __global__ void __launch_bounds__(kGsThreads, 6) gs_sweep_kernel(const GsParams 
         const uint64_t pol_last = policy_evict_last();
         const float4 *s4 = reinterpret_cast<const float4 *>(base);
         const float *park = reinterpret_cast<const float *>(park4) + tid * 4;
-        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
+        f2 below2 = pk(0.0f, 0.0f);
+        auto classify4 = [&](const float4 &q, uint32_t &hits4) {   // hits4: bits 0..3 of this float4
             const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
             has_nan |= (mx != mx);
-            below += (q.x < plo_f) ? 1u : 0u;
-            below += (q.y < plo_f) ? 1u : 0u;
-            below += (q.z < plo_f) ? 1u : 0u;
-            below += (q.w < plo_f) ? 1u : 0u;
-            if (q.x >= plo_f && q.x <= phi_f) hits |= 1u << sh;
-            if (q.y >= plo_f && q.y <= phi_f) hits |= 2u << sh;
-            if (q.z >= plo_f && q.z <= phi_f) hits |= 4u << sh;
-            if (q.w >= plo_f && q.w <= phi_f) hits |= 8u << sh;
+            below2 = add2(below2, pk(fset_lt(q.x, plo_f), fset_lt(q.y, plo_f)));   // exact: counts << 2^24
+            below2 = add2(below2, pk(fset_lt(q.z, plo_f), fset_lt(q.w, plo_f)));
+            or_if_in_range<1u>(hits4, q.x, plo_f, phi_f);
+            or_if_in_range<2u>(hits4, q.y, plo_f, phi_f);
+            or_if_in_range<4u>(hits4, q.z, plo_f, phi_f);
+            or_if_in_range<8u>(hits4, q.w, plo_f, phi_f);
+        };
+        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
+            uint32_t h4 = 0;
+            classify4(q, h4);
+            hits |= h4 << sh;
         };
         auto append = [&](uint32_t hits) {
             const uint32_t cnt = static_cast<uint32_t>(__popc(hits));
@@ -197,6 +201,9 @@ __global__ void __launch_bounds__(kGsThreads, 6) gs_sweep_kernel(const GsParams 
             }
             append(hits);
         }
+        float b_lo, b_hi;
+        unpk(below2, b_lo, b_hi);
+        below = static_cast<uint32_t>(b_lo + b_hi);
     } else {
         for (int j = tid; j < len; j += THREADS) {
             const float x = __ldg(base + j);

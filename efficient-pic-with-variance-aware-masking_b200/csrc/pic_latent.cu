@@ -92,6 +92,12 @@ struct SliceParams {
 // diagnostics: units whose sampled bracket missed (counted since library load)
 __device__ unsigned long long g_fallback_units = 0ull;
 __device__ unsigned long long g_sampled_units = 0ull;
+#ifdef PIC_PHASE_TIMING
+__device__ long long g_phase_clk[16];
+#define PIC_PHASE(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == PIC_PHASE_BLOCK) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PIC_PHASE(i) do {} while (0)
+#endif
 
 struct SelectState {
     uint32_t lo, hi;
@@ -316,9 +322,10 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
                                                uint32_t *hist, uint32_t *cand, uint32_t *scratch,
                                                uint32_t &a_key, uint32_t &b_key) {
     const int tid = threadIdx.x;
-    int S = n >> 3;
-    S = S < 1024 ? 1024 : (S > kCandMax ? kCandMax : S);
+    int S = n >> 4;                    // ~6 % of the unit's cache lines are touched by the sample
+    S = S < 1024 ? 1024 : (S > kSampleMax ? kSampleMax : S);
     S &= ~3;
+    PIC_PHASE(0);
     // ---- 1. sample ----------------------------------------------------------------------
     if (VEC) {
         const int nvec = n >> 2, S4 = S >> 2;
@@ -339,10 +346,11 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         }
     }
     __syncthreads();
+    PIC_PHASE(1);
     // ---- 2. pivots: sample ranks kt -+ 4 sigma, resolved together to 22-bit buckets --------
     const float frac = static_cast<float>(lo) / static_cast<float>(n > 1 ? n - 1 : 1);
     const float kt = frac * static_cast<float>(S - 1);
-    const float margin = 4.0f * sqrtf(static_cast<float>(S) * frac * (1.0f - frac)) + 4.0f;
+    const float margin = 3.5f * sqrtf(static_cast<float>(S) * frac * (1.0f - frac)) + 4.0f;
     const int klo = static_cast<int>(floorf(kt - margin));
     const int khi = static_cast<int>(ceilf(kt + margin));
     uint32_t plo_key, phi_key;
@@ -353,6 +361,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
     const float phi_f = (khi < S - 1) ? key_to_float(phi_key) : INFINITY;
     if (tid == 0) { scratch[40] = 0u; scratch[41] = 0u; }
     __syncthreads();  // cand (the sample) may now be overwritten
+    PIC_PHASE(2);
     // ---- 3. sweep: count below, append the bracket's keys ------------------------------------
     // float-domain compares (== key order for non-NaN, -0 == +0); NaN fails every compare.
     // Each iteration's values are parked in the (currently idle) histogram region of shared
@@ -367,17 +376,21 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
         float4 *park4 = reinterpret_cast<float4 *>(hist);
         const float *park = reinterpret_cast<const float *>(hist) + tid * 4;
-        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
+        f2 below2 = pk(0.0f, 0.0f);
+        auto classify4 = [&](const float4 &q, uint32_t &hits4) {   // hits4: bits 0..3 of this float4
             const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
             has_nan |= (mx != mx);
-            below += (q.x < plo_f) ? 1u : 0u;
-            below += (q.y < plo_f) ? 1u : 0u;
-            below += (q.z < plo_f) ? 1u : 0u;
-            below += (q.w < plo_f) ? 1u : 0u;
-            if (q.x >= plo_f && q.x <= phi_f) hits |= 1u << sh;
-            if (q.y >= plo_f && q.y <= phi_f) hits |= 2u << sh;
-            if (q.z >= plo_f && q.z <= phi_f) hits |= 4u << sh;
-            if (q.w >= plo_f && q.w <= phi_f) hits |= 8u << sh;
+            below2 = add2(below2, pk(fset_lt(q.x, plo_f), fset_lt(q.y, plo_f)));   // exact: counts << 2^24
+            below2 = add2(below2, pk(fset_lt(q.z, plo_f), fset_lt(q.w, plo_f)));
+            or_if_in_range<1u>(hits4, q.x, plo_f, phi_f);
+            or_if_in_range<2u>(hits4, q.y, plo_f, phi_f);
+            or_if_in_range<4u>(hits4, q.z, plo_f, phi_f);
+            or_if_in_range<8u>(hits4, q.w, plo_f, phi_f);
+        };
+        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
+            uint32_t h4 = 0;
+            classify4(q, h4);
+            hits |= h4 << sh;
         };
         auto append = [&](uint32_t hits) {   // bit e -> park[(e >> 2) * THREADS * 4 + (e & 3)]
             // one slot reservation per WARP (inclusive shuffle scan of the hit counts): the
@@ -428,6 +441,9 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
             }
             append(hits);
         }
+        float b_lo, b_hi;
+        unpk(below2, b_lo, b_hi);
+        below = static_cast<uint32_t>(b_lo + b_hi);
     } else {
         for (int j = tid; j < n; j += THREADS) {
             const float x = __ldg(std_u + j);
@@ -444,6 +460,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
     if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
     __syncthreads();
     const uint32_t c_cand = scratch[40], c_below = scratch[41];
+    PIC_PHASE(3);
     // ---- 4. exact ranks among the candidates ------------------------------------------------
     const bool valid = c_cand <= static_cast<uint32_t>(kCandMax) && c_below <= lo && hi < c_below + c_cand;
     if (!valid) {
@@ -455,6 +472,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
     const uint32_t width = float_to_key(phi_f) - base;
     block_select_norm<THREADS>(cand, static_cast<int>(c_cand), base, 32 - __clz(width | 1u), hist, scratch,
                                lo - c_below, hi - c_below, a_key, b_key);
+    PIC_PHASE(4);
     return true;
 }
 
@@ -475,7 +493,7 @@ constexpr size_t fused_dyn_smem() {
 }
 
 template <bool TRAIN, bool VEC, int THREADS, int OUTS>
-__global__ void __launch_bounds__(THREADS, (OUTS == kOutsSelectOnly ? 1536 : 1024) / THREADS)
+__global__ void __launch_bounds__(THREADS, (OUTS == kOutsSelectOnly ? 1280 : 1024) / THREADS)
 slice_fused_kernel(const SliceParams p) {
     __shared__ __align__(16) FusedSmem<THREADS> sm;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -1269,6 +1287,13 @@ int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, 
     *n_kernels = 1;                              // single fused kernel
     return 0;
 }
+
+#ifdef PIC_PHASE_TIMING
+extern "C" int pic_debug_phase_clocks(long long *out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback) {
     PIC_CUDA_CHECK(cudaDeviceSynchronize());

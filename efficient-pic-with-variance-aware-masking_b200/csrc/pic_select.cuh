@@ -116,7 +116,8 @@ __device__ __forceinline__ uint32_t block_next_nonempty(const uint32_t *hist, in
     return r;
 }
 
-constexpr int kCandMax = 4096;  // candidate buffer (keys of the pivot bracket / chosen bucket)
+constexpr int kCandMax = 5120;    // candidate buffer (keys of the pivot bracket / chosen bucket)
+constexpr int kSampleMax = 2048;  // sample size of the sampled-pivot select (bracket ~ 8 % of the unit)
 
 // Key sources for the block-level passes: keys already in shared memory, or a unit's std
 // values in global memory (converted on the fly; L2-resident after the first sweep).

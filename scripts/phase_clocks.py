@@ -1,0 +1,20 @@
+import ctypes, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+L = ctypes.CDLL(os.path.join(ROOT, "dbg_libpic_phase.so"))
+vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
+L.pic_select_threshold.argtypes = [vp, i64, i64, f32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+dev = torch.device("cuda:0")
+n = 49152
+_, _, _, std_all = bench.make_device_inputs(torch, n, 2048, 1, dev)
+for units in (1, 148, 888, 2048):
+    std = std_all[:units]
+    thr = torch.empty(units, device=dev)
+    for _ in range(3):
+        L.pic_select_threshold(std.data_ptr(), n, units, 0.5, None, thr.data_ptr(), None, None, None, 0, torch.cuda.current_stream().cuda_stream)
+    clk = (ctypes.c_longlong * 16)()
+    L.pic_debug_phase_clocks(clk)
+    c = list(clk)[:5]
+    d = [(c[i + 1] - c[i]) for i in range(4)]
+    print(f"units={units:5d} cycles: sample {d[0]:7d}  pivots {d[1]:7d}  sweep {d[2]:7d}  final {d[3]:7d}  total {c[4]-c[0]:7d}  (~{(c[4]-c[0])/1.965e3:.1f} us)")
