@@ -818,7 +818,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) gaussian_forward_kernel(const float *inputs, const float *scales,
                                                                const float *means, const float *noise,
                                                                int64_t n, float scale_bound, float lik_bound,
-                                                               float *outputs, float *lik) {
+                                                               float *outputs, float *lik, bool vec) {
     const float lb = (KIND == 2) ? 0.0f : lik_bound;
     auto quant = [&](float x, float mu, float nz, float &out, float &value) {
         if (KIND == 1) {
@@ -832,10 +832,34 @@ __global__ void __launch_bounds__(256) gaussian_forward_kernel(const float *inpu
         }
         value = means ? __fsub_rn(out, mu) : out;
     };
-    // two elements per iteration through the packed-f32 likelihood (pic_fast.cuh)
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+        // 128-bit accesses, two packed-f32 likelihood pairs per float4 (pic_fast.cuh)
+        const int64_t nvec = n >> 2;
+        for (int64_t j = t0; j < nvec; j += stride) {
+            const float4 x4 = __ldg(reinterpret_cast<const float4 *>(inputs) + j);
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(scales) + j);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 m4 = means ? __ldg(reinterpret_cast<const float4 *>(means) + j) : z;
+            const float4 n4 = (KIND == 1) ? __ldg(reinterpret_cast<const float4 *>(noise) + j) : z;
+            const float x[4] = {x4.x, x4.y, x4.z, x4.w}, sc[4] = {s4.x, s4.y, s4.z, s4.w};
+            const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, nz[4] = {n4.x, n4.y, n4.z, n4.w};
+            float o[4], v[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) quant(x[e], mu[e], nz[e], o[e], v[e]);
+            if (outputs) reinterpret_cast<float4 *>(outputs)[j] = make_float4(o[0], o[1], o[2], o[3]);
+            if (lik) {
+                likelihood_pair(fabsf(v[0]), fabsf(v[1]), max_nan(sc[0], scale_bound), max_nan(sc[1], scale_bound), lb, l[0], l[1]);
+                likelihood_pair(fabsf(v[2]), fabsf(v[3]), max_nan(sc[2], scale_bound), max_nan(sc[3], scale_bound), lb, l[2], l[3]);
+                reinterpret_cast<float4 *>(lik)[j] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        return;
+    }
+    // scalar path: two elements per iteration through the packed-f32 likelihood
     const int64_t pairs = n >> 1;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < pairs; j += stride) {
+    for (int64_t j = t0; j < pairs; j += stride) {
         const int64_t i0 = 2 * j, i1 = i0 + 1;
         float o0, o1, v0, v1;
         quant(inputs[i0], means ? means[i0] : 0.0f, (KIND == 1) ? noise[i0] : 0.0f, o0, v0);
@@ -899,54 +923,111 @@ __global__ void __launch_bounds__(256) gaussian_backward_kernel(const float *g_o
 }
 
 __global__ void __launch_bounds__(256) build_indexes_kernel(const float *scales, int64_t n, const float *table,
-                                                            int table_len, float scale_bound, int32_t *idx) {
-    __shared__ float tbl[kTableSmem];
-    const bool tbl64 = table_len == kTableSmem;
-    if (tbl64 && threadIdx.x < kTableSmem) tbl[threadIdx.x] = table[threadIdx.x];
+                                                            int table_len, float scale_bound, int32_t *idx, bool vec) {
+    __shared__ __align__(16) float sm[kIndexSmemFloats];
+    SliceParams p{};
+    p.table = table;
+    p.table_len = table_len;
+    p.idx = idx;
+    const IndexCtx ic = index_ctx_setup(p, sm);   // shared table copy + MUFU.LG2 guess parameters
     __syncthreads();
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const float s = scales[j];
-        idx[j] = tbl64 ? scale_index64(s, scale_bound, tbl) : scale_index(s, scale_bound, table, table_len);
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t nvec = n >> 2;
+        for (int64_t j = t0; j < nvec; j += stride) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(scales) + j);
+            reinterpret_cast<int4 *>(idx)[j] =
+                make_int4(scale_index_fast(max_nan(s4.x, scale_bound), ic), scale_index_fast(max_nan(s4.y, scale_bound), ic),
+                          scale_index_fast(max_nan(s4.z, scale_bound), ic), scale_index_fast(max_nan(s4.w, scale_bound), ic));
+        }
+        return;
     }
+    for (int64_t j = t0; j < n; j += stride) idx[j] = scale_index_fast(max_nan(scales[j], scale_bound), ic);
 }
 
+__device__ __forceinline__ float quantize_one(float x, float mu, float nz, float mk, int mode, bool has_mean,
+                                              bool has_mask) {
+    if (mode == PIC_QUANTIZE_NOISE) return __fadd_rn(x, has_mask ? __fmul_rn(nz, mk) : nz);
+    if (mode == PIC_QUANTIZE_STE) return __fadd_rn(__fsub_rn(rintf(x), x), x);
+    const float t = rintf(has_mean ? __fsub_rn(x, mu) : x);
+    if (mode == PIC_QUANTIZE_DEQUANTIZE) return has_mean ? __fadd_rn(t, mu) : t;
+    return t;  // PIC_QUANTIZE_SYMBOLS: the caller converts to int32
+}
+
+// vec: n % 4 == 0 and every pointer 16-byte aligned -> one 128-bit access per tensor and thread
 __global__ void __launch_bounds__(256) quantize_kernel(const float *inputs, const float *means, const float *noise,
                                                        const float *mask, int64_t n, int mode, float *out_f,
-                                                       int32_t *out_i) {
+                                                       int32_t *out_i, bool vec) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const float x = inputs[j];
-        if (mode == PIC_QUANTIZE_NOISE) {
-            const float nz = mask ? __fmul_rn(noise[j], mask[j]) : noise[j];
-            out_f[j] = __fadd_rn(x, nz);
-            continue;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool has_mean = means != nullptr, has_mask = mask != nullptr, is_noise = mode == PIC_QUANTIZE_NOISE;
+    if (vec) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t j = t0; j < (n >> 2); j += stride) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(inputs) + j);
+            const float4 m = (has_mean && !is_noise) ? __ldg(reinterpret_cast<const float4 *>(means) + j) : z;
+            const float4 nz = is_noise ? __ldg(reinterpret_cast<const float4 *>(noise) + j) : z;
+            const float4 mk = (is_noise && has_mask) ? __ldg(reinterpret_cast<const float4 *>(mask) + j) : z;
+            const float4 r = make_float4(quantize_one(x.x, m.x, nz.x, mk.x, mode, has_mean, has_mask),
+                                         quantize_one(x.y, m.y, nz.y, mk.y, mode, has_mean, has_mask),
+                                         quantize_one(x.z, m.z, nz.z, mk.z, mode, has_mean, has_mask),
+                                         quantize_one(x.w, m.w, nz.w, mk.w, mode, has_mean, has_mask));
+            if (mode == PIC_QUANTIZE_SYMBOLS)
+                reinterpret_cast<int4 *>(out_i)[j] =
+                    make_int4(__float2int_rn(r.x), __float2int_rn(r.y), __float2int_rn(r.z), __float2int_rn(r.w));
+            else
+                reinterpret_cast<float4 *>(out_f)[j] = r;
         }
-        if (mode == PIC_QUANTIZE_STE) {
-            out_f[j] = __fadd_rn(__fsub_rn(rintf(x), x), x);
-            continue;
-        }
-        float t = means ? __fsub_rn(x, means[j]) : x;
-        t = rintf(t);
-        if (mode == PIC_QUANTIZE_DEQUANTIZE) out_f[j] = means ? __fadd_rn(t, means[j]) : t;
-        else out_i[j] = __float2int_rn(t);
+        return;
+    }
+    for (int64_t j = t0; j < n; j += stride) {
+        const float r = quantize_one(inputs[j], (has_mean && !is_noise) ? means[j] : 0.0f, is_noise ? noise[j] : 0.0f,
+                                     (is_noise && has_mask) ? mask[j] : 0.0f, mode, has_mean, has_mask);
+        if (mode == PIC_QUANTIZE_SYMBOLS) out_i[j] = __float2int_rn(r);
+        else out_f[j] = r;
     }
 }
 
 __global__ void __launch_bounds__(256) dequantize_kernel(const int32_t *symbols, const float *means, int64_t n,
-                                                         float *out) {
+                                                         float *out, bool vec) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (int64_t j = t0; j < (n >> 2); j += stride) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(symbols) + j);
+            float4 v = make_float4(static_cast<float>(q.x), static_cast<float>(q.y), static_cast<float>(q.z),
+                                   static_cast<float>(q.w));
+            if (means) {
+                const float4 m = __ldg(reinterpret_cast<const float4 *>(means) + j);
+                v = make_float4(__fadd_rn(v.x, m.x), __fadd_rn(v.y, m.y), __fadd_rn(v.z, m.z), __fadd_rn(v.w, m.w));
+            }
+            reinterpret_cast<float4 *>(out)[j] = v;
+        }
+        return;
+    }
+    for (int64_t j = t0; j < n; j += stride) {
         const float v = static_cast<float>(symbols[j]);
         out[j] = means ? __fadd_rn(v, means[j]) : v;
     }
 }
 
+// vec: n_per_unit % 4 == 0 and aligned pointers, so a float4 never straddles two units
 __global__ void __launch_bounds__(256) mask_from_threshold_kernel(const float *std, const float *thr,
                                                                   int64_t n_per_unit, int64_t total,
-                                                                  float *mask) {
+                                                                  float *mask, bool vec) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (int64_t j = t0; j < (total >> 2); j += stride) {
+            const float t = __ldg(thr + (4 * j) / n_per_unit);
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(std) + j);
+            reinterpret_cast<float4 *>(mask)[j] = make_float4((s.x >= t) ? 1.0f : 0.0f, (s.y >= t) ? 1.0f : 0.0f,
+                                                              (s.z >= t) ? 1.0f : 0.0f, (s.w >= t) ? 1.0f : 0.0f);
+        }
+        return;
+    }
+    for (int64_t j = t0; j < total; j += stride) {
         const float t = thr[j / n_per_unit];
         mask[j] = (std[j] >= t) ? 1.0f : 0.0f;
     }
@@ -1425,8 +1506,9 @@ int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_un
                             pic_stream_t stream_) {
     if (n_per_unit <= 0 || units <= 0 || !std || !thr || !mask) return PIC_ERR_INVALID_ARGUMENT;
     const int64_t total = n_per_unit * units;
-    mask_from_threshold_kernel<<<elementwise_grid(total), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        std, thr, n_per_unit, total, mask);
+    const bool vec = (n_per_unit % 4 == 0) && aligned16(std) && aligned16(mask);
+    mask_from_threshold_kernel<<<elementwise_grid(total, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        std, thr, n_per_unit, total, mask, vec);
     return launch_status();
 }
 
@@ -1526,10 +1608,14 @@ int pic_gaussian_forward(const float *inputs, const float *scales, const float *
                          float *lik, pic_stream_t stream_) {
     if (n <= 0 || !inputs || !scales) return PIC_ERR_INVALID_ARGUMENT;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int grid = elementwise_grid(n, 2);
-    if (likelihood_only) gaussian_forward_kernel<2><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
-    else if (noise) gaussian_forward_kernel<1><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
-    else gaussian_forward_kernel<0><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik);
+    const int grid = elementwise_grid(n, 4);
+    bool vec = (n % 4 == 0);
+    for (const void *q : {static_cast<const void *>(inputs), static_cast<const void *>(scales), static_cast<const void *>(means),
+                          static_cast<const void *>(noise), static_cast<const void *>(outputs), static_cast<const void *>(lik)})
+        if (q && !aligned16(q)) vec = false;
+    if (likelihood_only) gaussian_forward_kernel<2><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik, vec);
+    else if (noise) gaussian_forward_kernel<1><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik, vec);
+    else gaussian_forward_kernel<0><<<grid, 256, 0, stream>>>(inputs, scales, means, noise, n, scale_bound, lik_bound, outputs, lik, vec);
     return launch_status();
 }
 
@@ -1549,8 +1635,9 @@ int pic_gaussian_backward(const float *g_out, const float *g_lik, const float *i
 int pic_build_indexes(const float *scales, int64_t n, const float *scale_table, int table_len, float scale_bound,
                       int32_t *idx, pic_stream_t stream_) {
     if (n <= 0 || !scales || !scale_table || table_len < 1 || !idx) return PIC_ERR_INVALID_ARGUMENT;
-    build_indexes_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        scales, n, scale_table, table_len, scale_bound, idx);
+    const bool vec = (n % 4 == 0) && aligned16(scales) && aligned16(idx);
+    build_indexes_kernel<<<elementwise_grid(n, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        scales, n, scale_table, table_len, scale_bound, idx, vec);
     return launch_status();
 }
 
@@ -1561,14 +1648,20 @@ int pic_quantize(const float *inputs, const float *means, const float *noise, co
     if (mode == PIC_QUANTIZE_NOISE && (!noise || !out_f32)) return PIC_ERR_INVALID_ARGUMENT;
     if ((mode == PIC_QUANTIZE_DEQUANTIZE || mode == PIC_QUANTIZE_STE) && !out_f32) return PIC_ERR_INVALID_ARGUMENT;
     if (mode == PIC_QUANTIZE_SYMBOLS && !out_i32) return PIC_ERR_INVALID_ARGUMENT;
-    quantize_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(inputs, means, noise, mask, n,
-                                                                                      mode, out_f32, out_i32);
+    bool vec = (n % 4 == 0);
+    for (const void *q : {static_cast<const void *>(inputs), static_cast<const void *>(means), static_cast<const void *>(noise),
+                          static_cast<const void *>(mask), static_cast<const void *>(out_f32), static_cast<const void *>(out_i32)})
+        if (q && !aligned16(q)) vec = false;
+    quantize_kernel<<<elementwise_grid(n, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        inputs, means, noise, mask, n, mode, out_f32, out_i32, vec);
     return launch_status();
 }
 
 int pic_dequantize(const int32_t *symbols, const float *means, int64_t n, float *out, pic_stream_t stream_) {
     if (n <= 0 || !symbols || !out) return PIC_ERR_INVALID_ARGUMENT;
-    dequantize_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream_)>>>(symbols, means, n, out);
+    const bool vec = (n % 4 == 0) && aligned16(symbols) && aligned16(out) && (!means || aligned16(means));
+    dequantize_kernel<<<elementwise_grid(n, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(symbols, means, n,
+                                                                                                       out, vec);
     return launch_status();
 }
 

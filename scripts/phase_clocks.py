@@ -1,8 +1,16 @@
-import ctypes, os, sys, torch
+"""clock64() phase breakdown of the sampled select (debug build with -DPIC_PHASE_TIMING, built on the fly)."""
+import ctypes, os, subprocess, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-L = ctypes.CDLL(os.path.join(ROOT, "dbg_libpic_phase.so"))
+SO = os.path.join(ROOT, "gpurun_out", "libpic_phase_dbg.so")
+if not os.path.isfile(SO):
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    csrc = os.path.join(ROOT, "efficient-pic-with-variance-aware-masking_b200", "csrc")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                    "-DPIC_PHASE_TIMING", "-DPIC_PHASE_BLOCK=0", "-o", SO, os.path.join(csrc, "pic_latent.cu"),
+                    os.path.join(csrc, "pic_host.cu")], check=True)
+L = ctypes.CDLL(SO)
 vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
 L.pic_select_threshold.argtypes = [vp, i64, i64, f32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
 dev = torch.device("cuda:0")

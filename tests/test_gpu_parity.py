@@ -518,3 +518,35 @@ def test_progressive_levels(pic, dev):
     sym = torch.randint(-5, 6, level.shape, device=dev, dtype=torch.int32)
     lvl2 = torch.where(level == 2, sym, torch.zeros_like(sym))
     assert torch.equal(lvl2, sym * T(((lv == 2).astype(np.int32)).reshape(level.shape), dev))
+
+
+@pytest.mark.parametrize("n,offset", [(4096 * 33, 0), (4096 * 33, 1), (4096 * 33 + 3, 0), (7, 0)])
+def test_elementwise_kernels_vector_and_scalar_paths(pic, dev, n, offset):
+    """GaussianConditional's un-fused kernels (quantize / dequantize / build_indexes / likelihood / mask) take a
+    128-bit path when n % 4 == 0 and the pointers are 16-byte aligned, a scalar path otherwise: both vs the oracle."""
+    rng = np.random.default_rng(1234 + n + offset)
+    y, _, mu, std = trained_like(rng, (1, n))
+    y, mu, std = y.reshape(-1), mu.reshape(-1), std.reshape(-1)
+    noise = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    table_np = scale_table()
+
+    def D(a):  # device copy whose pointer is offset by `offset` floats from a 256-byte aligned allocation
+        t = torch.empty(a.size + offset, dtype=torch.from_numpy(a).dtype, device=dev)
+        t[offset:] = T(a, dev)
+        return t[offset:]
+
+    assert np.array_equal(N(pic.ops.build_indexes(D(std), T(table_np, dev))), po.build_indexes(std, table_np))
+    for mode, kw in (("symbols", dict(means=mu)), ("dequantize", dict(means=mu)), ("dequantize", {}),
+                     ("noise", dict(noise=noise)), ("noise", dict(noise=noise, mask=(std > 1).astype(np.float32)))):
+        got = pic.ops.quantize(D(y), mode, **{k: D(v) for k, v in kw.items()})
+        assert np.array_equal(N(got), po.quantize(y, mode, **kw)), (mode, list(kw))
+    sym = po.quantize(y, "symbols", means=mu)
+    assert np.array_equal(N(pic.ops.dequantize(D(sym), D(mu))), sym.astype(np.float32) + mu)
+    assert np.array_equal(N(pic.ops.dequantize(D(sym))), sym.astype(np.float32))
+    for nz in (None, noise):
+        out, lik = pic.ops.gaussian_forward(D(y), D(std), D(mu), None if nz is None else D(nz))
+        ref_out, ref_lik = po.gaussian_forward(y, std, mu, nz)
+        assert np.array_equal(N(out), ref_out)
+        assert_lik_close(N(lik), ref_lik)
+    thr = np.array([np.float32(np.median(std))], dtype=np.float32)
+    assert np.array_equal(N(pic.ops.mask_from_threshold(D(std), T(thr, dev), 1)), (std >= thr[0]).astype(np.float32))
