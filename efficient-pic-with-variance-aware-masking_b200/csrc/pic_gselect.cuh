@@ -29,9 +29,11 @@ struct GsParams {
     float q01;
     int64_t n, units;
     GsUnit *st;
-    uint32_t *cand;        // [units][kCandMax]
+    uint32_t *cand;        // [units][cand_cap]
     float *thr, *a_out, *b_out;
     int vec;
+    int64_t cand_cap;      // kCandMax for fused-size units; n/8 for large units (candidates as raw floats)
+    uint32_t *below_tile;  // large units: [units][tiles] per-tile counts below the bracket (no atomics), else null
 };
 
 __global__ void __launch_bounds__(kGsThreads, 5) gs_pivot_kernel(const GsParams p) {
@@ -119,11 +121,18 @@ __global__ void __launch_bounds__(kGsThreads, 5) gs_pivot_kernel(const GsParams 
     if (tid == 0) p.st[u] = st;
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(kGsThreads, 6) gs_sweep_kernel(const GsParams p, int tiles_per_unit) {
+// RAW: candidates are stored as float bits (input of the histogram rounds) instead of ordered keys.
+// One CTA per 8192-element tile: the tile is parked in shared memory while it is classified (one hit bit per
+// element in a register), then ONE global reservation per CTA places the tile's bracket elements in the unit's
+// candidate buffer (per-warp reservations serialise on the unit's counter once units are millions of elements).
+template <bool VEC, bool RAW>
+__global__ void __launch_bounds__(kGsThreads, 4) gs_sweep_kernel(const GsParams p, int tiles_per_unit) {
     constexpr int THREADS = kGsThreads;
-    __shared__ __align__(16) float4 park4[4 * THREADS];   // 16 KB: per-thread private slots
-    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(kGsTile == 32 * THREADS, "one hit bit per element and thread");
+    __shared__ __align__(16) float4 park4[kGsTile / 4];   // 32 KB: the CTA's tile
+    __shared__ uint32_t warp_off[WARPS + 1], warp_below[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t u = blockIdx.x / tiles_per_unit;
     const int tile = blockIdx.x - static_cast<int>(u) * tiles_per_unit;
     GsUnit *st = p.st + u;
@@ -132,91 +141,101 @@ __global__ void __launch_bounds__(kGsThreads, 6) gs_sweep_kernel(const GsParams 
     const int64_t begin = static_cast<int64_t>(tile) * kGsTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kGsTile), p.n - begin));
     const float *base = p.std + u * p.n + begin;
-    uint32_t *cand = p.cand + u * kCandMax;
-    uint32_t below = 0;
+    uint32_t *cand = p.cand + u * p.cand_cap;
+    const uint32_t cap = static_cast<uint32_t>(p.cand_cap);
+    const float *parkf = reinterpret_cast<const float *>(park4);
+    uint32_t below = 0, hits = 0;
     bool has_nan = false;
-    if (VEC) {
-        const int nvec = len >> 2;
+    if (VEC) {   // bit 4*i + e  <->  element e of float4 (i * THREADS + tid)
+        const int nvec = len >> 2;   // VEC: n % 4 == 0, so every tile is whole float4s
         const uint64_t pol_last = policy_evict_last();
         const float4 *s4 = reinterpret_cast<const float4 *>(base);
-        const float *park = reinterpret_cast<const float *>(park4) + tid * 4;
         f2 below2 = pk(0.0f, 0.0f);
-        auto classify4 = [&](const float4 &q, uint32_t &hits4) {   // hits4: bits 0..3 of this float4
+        auto classify = [&](const float4 &q, int sh) {
             const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
             has_nan |= (mx != mx);
             below2 = add2(below2, pk(fset_lt(q.x, plo_f), fset_lt(q.y, plo_f)));   // exact: counts << 2^24
             below2 = add2(below2, pk(fset_lt(q.z, plo_f), fset_lt(q.w, plo_f)));
-            or_if_in_range<1u>(hits4, q.x, plo_f, phi_f);
-            or_if_in_range<2u>(hits4, q.y, plo_f, phi_f);
-            or_if_in_range<4u>(hits4, q.z, plo_f, phi_f);
-            or_if_in_range<8u>(hits4, q.w, plo_f, phi_f);
-        };
-        auto classify = [&](const float4 &q, uint32_t &hits, int sh) {
             uint32_t h4 = 0;
-            classify4(q, h4);
+            or_if_in_range<1u>(h4, q.x, plo_f, phi_f);
+            or_if_in_range<2u>(h4, q.y, plo_f, phi_f);
+            or_if_in_range<4u>(h4, q.z, plo_f, phi_f);
+            or_if_in_range<8u>(h4, q.w, plo_f, phi_f);
             hits |= h4 << sh;
         };
-        auto append = [&](uint32_t hits) {
-            const uint32_t cnt = static_cast<uint32_t>(__popc(hits));
-            if (__ballot_sync(0xffffffffu, cnt != 0u) == 0u) return;
-            uint32_t incl = cnt;
+        if (nvec == kGsTile / 4) {
+            float4 v[8];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            uint32_t pos0 = 0;
-            if (lane == 31) pos0 = atomicAdd(&st->c_cand, incl);   // one global reservation per warp
-            pos0 = __shfl_sync(0xffffffffu, pos0, 31);
-            uint32_t pos = pos0 + incl - cnt;
-            while (hits) {
-                const int e = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const float x = park[(e >> 2) * (THREADS * 4) + (e & 3)];
-                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = float_to_key(x);
-                ++pos;
-            }
-        };
-        int jb = tid - lane;
-        for (; jb + 3 * THREADS + 31 < nvec; jb += 4 * THREADS) {
-            const int j = jb + lane;
-            float4 v[4];
+            for (int i = 0; i < 8; ++i) v[i] = ld_hint(s4 + tid + i * THREADS, pol_last);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = ld_hint(s4 + j + i * THREADS, pol_last);
-            uint32_t hits = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 park4[i * THREADS + tid] = v[i];
-                classify(v[i], hits, 4 * i);
+                classify(v[i], 4 * i);
             }
-            append(hits);
-        }
-        for (; jb < nvec; jb += THREADS) {
-            const int j = jb + lane;
-            uint32_t hits = 0;
-            if (j < nvec) {
-                const float4 v0 = ld_hint(s4 + j, pol_last);
-                park4[tid] = v0;
-                classify(v0, hits, 0);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                const int j = tid + i * THREADS;
+                if (j < nvec) {
+                    const float4 v = ld_hint(s4 + j, pol_last);
+                    park4[j] = v;
+                    classify(v, 4 * i);
+                }
             }
-            append(hits);
         }
         float b_lo, b_hi;
         unpk(below2, b_lo, b_hi);
         below = static_cast<uint32_t>(b_lo + b_hi);
-    } else {
-        for (int j = tid; j < len; j += THREADS) {
-            const float x = __ldg(base + j);
-            has_nan |= (x != x);
-            below += (x < plo_f) ? 1u : 0u;
-            if (x >= plo_f && x <= phi_f) {
-                const uint32_t pos = atomicAdd(&st->c_cand, 1u);
-                if (pos < static_cast<uint32_t>(kCandMax)) cand[pos] = float_to_key(x);
+    } else {     // bit i  <->  element i * THREADS + tid
+        float *parkw = reinterpret_cast<float *>(park4);
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int j = tid + i * THREADS;
+            if (j < len) {
+                const float x = __ldg(base + j);
+                parkw[j] = x;
+                has_nan |= (x != x);
+                below += (x < plo_f) ? 1u : 0u;
+                if (x >= plo_f && x <= phi_f) hits |= 1u << i;
             }
         }
     }
+    // CTA-wide reservation: warp scan -> per-warp offsets -> one atomicAdd on the unit's counter
+    const uint32_t cnt = static_cast<uint32_t>(__popc(hits));
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
     below = __reduce_add_sync(0xffffffffu, below);
-    if (lane == 0 && below) atomicAdd(&st->c_below, below);
+    if (lane == 31) {
+        warp_off[warp] = incl;
+        warp_below[warp] = below;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0, bsum = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = warp_off[w];
+            warp_off[w] = run;
+            run += c;
+            bsum += warp_below[w];
+        }
+        warp_off[WARPS] = run ? atomicAdd(&st->c_cand, run) : 0u;
+        if (p.below_tile) p.below_tile[blockIdx.x] = bsum;          // summed by gs_begin_rounds_kernel
+        else if (bsum) atomicAdd(&st->c_below, bsum);
+    }
+    __syncthreads();
+    uint32_t pos = warp_off[WARPS] + warp_off[warp] + incl - cnt;
+    while (hits) {
+        const int e = __ffs(hits) - 1;
+        hits &= hits - 1u;
+        const float x = VEC ? parkf[((e >> 2) * THREADS + tid) * 4 + (e & 3)] : parkf[e * THREADS + tid];
+        if (pos < cap) cand[pos] = RAW ? __float_as_uint(x) : float_to_key(x);
+        ++pos;
+    }
     if (__any_sync(0xffffffffu, has_nan) && lane == 0) atomicOr(&st->nan_flag, 1u);
 }
 
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(kGsThreads, 5) gs_finish_kernel(const GsParams
     uint32_t a_key, b_key;
     const bool valid = st.c_cand <= static_cast<uint32_t>(kCandMax) && st.c_below <= lo && hi < st.c_below + st.c_cand;
     if (valid) {
-        const uint32_t *gc = p.cand + u * kCandMax;
+        const uint32_t *gc = p.cand + u * p.cand_cap;
         for (int i = tid; i < static_cast<int>(st.c_cand); i += THREADS) cand[i] = gc[i];
         __syncthreads();
         const uint32_t base = float_to_key(st.plo_f);
@@ -257,6 +276,48 @@ __global__ void __launch_bounds__(kGsThreads, 5) gs_finish_kernel(const GsParams
         if (p.a_out) p.a_out[u] = a;
         if (p.b_out) p.b_out[u] = b;
     }
+}
+
+// Large units: after the sweep the exact ranks are found by the histogram rounds (hist_round_kernel /
+// select_advance_kernel) over the unit's candidate buffer -- or, when the bracket missed or overflowed, over
+// the whole unit (same launches, graceful fallback).  One thread per unit sets up the round state.
+__global__ void __launch_bounds__(128) gs_begin_rounds_kernel(const GsParams p, SelectState *state, int tiles_per_unit) {
+    __shared__ uint32_t red[4];
+    const int64_t u = blockIdx.x;
+    const int tid = threadIdx.x;
+    GsUnit g = p.st[u];
+    if (g.state == 0u && p.below_tile) {   // per-tile counts below the bracket -> c_below
+        uint32_t acc = 0;
+        for (int t = tid; t < tiles_per_unit; t += 128) acc += p.below_tile[u * tiles_per_unit + t];
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        g.c_below = red[0] + red[1] + red[2] + red[3];
+    }
+    if (tid != 0) return;
+    SelectState st{};
+    st.q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
+    if (g.state != 0u) {          // ones / zeros / tiny unit: threshold already written by gs_pivot_kernel
+        st.mode = kModeDone;
+        state[u] = st;
+        return;
+    }
+    st.mode = kModeThreshold;
+    quantile_ranks(st.q, p.n, st.lo, st.hi, st.w);
+    const bool valid = g.c_cand <= static_cast<uint32_t>(p.cand_cap) && g.c_below <= st.lo &&
+                       st.hi < g.c_below + g.c_cand;
+    if (valid) {
+        st.lo -= g.c_below;
+        st.hi -= g.c_below;
+        st.pad[0] = 1u;           // rounds read the candidate buffer ...
+        st.pad[1] = g.c_cand;     // ... of this many elements
+        atomicAdd(&g_sampled_units, 1ull);
+    } else {
+        atomicAdd(&g_fallback_units, 1ull);
+    }
+    st.rank = st.lo;
+    st.nan_flag = g.nan_flag;
+    state[u] = st;
 }
 
 }  // namespace pic

@@ -105,7 +105,7 @@ struct SelectState {
     uint32_t prefix, rank, below_total;
     uint32_t a_key, b_key, need_min, nan_flag, count;
     int32_t mode;
-    uint32_t pad[3];
+    uint32_t pad[3];   // [0] 1 = rounds read the unit's candidate buffer (large-unit sampled select), [1] its length
 };
 static_assert(sizeof(SelectState) == 64, "SelectState must stay 64 bytes");
 
@@ -593,15 +593,20 @@ __global__ void select_begin_kernel(SelectState *state, int64_t n_total, int64_t
 }
 
 // grid: (chunks, units).  hist: [units][kHistWords] (pre-zeroed); min_above: [units] (0xffffffff).
+// cand != nullptr: units whose state says so read their candidate buffer (raw floats, cand_cap per unit)
+// instead of std -- the large-unit sampled select; the other units (bracket fallback) read all of std.
 template <int ROUND, bool VEC>
 __global__ void __launch_bounds__(512) hist_round_kernel(const float *std, int64_t n_local,
                                                          const SelectState *state, uint32_t *hist,
-                                                         uint32_t *min_above) {
+                                                         uint32_t *min_above, const float *cand, int64_t cand_cap) {
     constexpr int THREADS = 512;
     __shared__ uint32_t sh[kHistBins];
     const int64_t u = blockIdx.y;
     const SelectState st = state[u];
     if (st.mode != kModeThreshold) return;
+    const bool from_cand = cand != nullptr && st.pad[0] != 0u;
+    if (from_cand) n_local = st.pad[1];
+    if (static_cast<int64_t>(blockIdx.x) * kRoundChunk >= n_local) return;
     constexpr int shift = round_shift(ROUND);
     constexpr int nbins = round_bins(ROUND);
     constexpr int up = shift + (ROUND == 1 ? 11 : 10);  // bits above this round's digit
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(512) hist_round_kernel(const float *std, int64
     __syncthreads();
     const int64_t begin = static_cast<int64_t>(blockIdx.x) * kRoundChunk;
     const int64_t end = min(n_local, begin + kRoundChunk);
-    const float *base = std + u * n_local;
+    const float *base = from_cand ? cand + u * cand_cap : std + u * n_local;
     const uint32_t want = (ROUND > 0) ? (st.prefix >> up) : 0u;
     uint32_t mn = 0xffffffffu;
     bool has_nan = false;
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(256) select_advance_kernel(SelectState *state,
     st.prefix |= hit.bin << round_shift(ROUND);
     st.rank -= hit.below;
     st.below_total += hit.below;
-    if (ROUND == 0) st.nan_flag = gh[kHistBins];
+    if (ROUND == 0) st.nan_flag |= gh[kHistBins];
     if (ROUND == 2) {
         st.a_key = st.prefix;
         st.count = hit.count;
@@ -696,6 +701,7 @@ __global__ void select_finish_kernel(const SelectState *state, const uint32_t *m
     if (u >= units) return;
     const SelectState st = state[u];
     float thr, a, b;
+    if (st.mode == kModeDone) return;   // written by gs_pivot_kernel
     if (st.mode == kModeOnes) {
         thr = a = b = -INFINITY;
     } else if (st.mode == kModeZeros) {
@@ -1226,12 +1232,13 @@ static int select_sampled_global(const float *std, int64_t n, int64_t units, flo
     g.cand = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(ws) + static_cast<size_t>(units) * sizeof(GsUnit));
     g.thr = thr; g.a_out = a_out; g.b_out = b_out;
     g.vec = ((n % 4 == 0) && aligned16(std)) ? 1 : 0;
+    g.cand_cap = kCandMax;
     const int tiles = static_cast<int>((n + kGsTile - 1) / kGsTile);
     if (units * tiles > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
     gs_pivot_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
     if (n > kCandMax) {
-        if (g.vec) gs_sweep_kernel<true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
-        else gs_sweep_kernel<false><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+        if (g.vec) gs_sweep_kernel<true, false><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+        else gs_sweep_kernel<false, false><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
         gs_finish_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
     }
     return launch_status();
@@ -1271,7 +1278,7 @@ static RoundsWs carve_ws(void *ws, int64_t units) {
 
 static int launch_hist_round(const float *std, int64_t n_local, int64_t units, int round,
                              const SelectState *state, uint32_t *hist, uint32_t *min_above,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const float *cand = nullptr, int64_t cand_cap = 0) {
     if (units > 65535) return PIC_ERR_TOO_LARGE;
     PIC_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(units) * kHistWords * 4, stream));
     if (round == 2) PIC_CUDA_CHECK(cudaMemsetAsync(min_above, 0xff, static_cast<size_t>(units) * 4, stream));
@@ -1279,8 +1286,8 @@ static int launch_hist_round(const float *std, int64_t n_local, int64_t units, i
     const bool vec = (n_local % 4 == 0) && aligned16(std);
     dim3 grid(static_cast<unsigned>((n_local + kRoundChunk - 1) / kRoundChunk), static_cast<unsigned>(units));
 #define PIC_LAUNCH_ROUND(R)                                                                                  \
-    if (vec) hist_round_kernel<R, true><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above);      \
-    else hist_round_kernel<R, false><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above)
+    if (vec) hist_round_kernel<R, true><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above, cand, cand_cap); \
+    else hist_round_kernel<R, false><<<grid, 512, 0, stream>>>(std, n_local, state, hist, min_above, cand, cand_cap)
     if (round == 0) { PIC_LAUNCH_ROUND(0); }
     else if (round == 1) { PIC_LAUNCH_ROUND(1); }
     else { PIC_LAUNCH_ROUND(2); }
@@ -1311,6 +1318,55 @@ static int select_rounds(const float *std, int64_t n, int64_t units, float q01, 
     select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
                                                                                       thr_out, a_out, b_out);
     return launch_status();
+}
+
+// Large units (> kFusedMaxElems) on one device: sampled pivots -> one tile-ordered sweep that counts the
+// elements below the bracket and compacts the bracket (~6 % of the unit) into a candidate buffer -> the three
+// histogram rounds over the candidates only.  Units whose bracket missed or overflowed run the same rounds over
+// the whole unit (exact either way).  ws layout: [rounds workspace][GsUnit x units][cand_cap floats x units][below counts x tiles x units].
+static int64_t large_cand_cap(int64_t n) { return ((n >> 3) + 3) & ~int64_t(3); }
+static size_t large_ws_bytes(int64_t n, int64_t units) {
+    const size_t rounds = (rounds_ws_bytes(units) + 255) / 256 * 256;
+    const size_t tiles = static_cast<size_t>((n + kGsTile - 1) / kGsTile);
+    return rounds + static_cast<size_t>(units) * (sizeof(GsUnit) + (static_cast<size_t>(large_cand_cap(n)) + tiles) * 4) + 512;
+}
+static int select_large(const float *std, int64_t n, int64_t units, float q01, const float *q01_per_unit,
+                        float *thr_out, float *a_out, float *b_out, void *ws, cudaStream_t stream) {
+    RoundsWs w = carve_ws(ws, units);
+    unsigned char *extra = static_cast<unsigned char *>(ws) + (rounds_ws_bytes(units) + 255) / 256 * 256;
+    GsParams g{};
+    g.std = std; g.q01_per_unit = q01_per_unit; g.q01 = q01; g.n = n; g.units = units;
+    g.st = reinterpret_cast<GsUnit *>(extra);
+    g.cand = reinterpret_cast<uint32_t *>(extra + (static_cast<size_t>(units) * sizeof(GsUnit) + 255) / 256 * 256);
+    g.thr = thr_out; g.a_out = a_out; g.b_out = b_out;
+    g.vec = ((n % 4 == 0) && aligned16(std)) ? 1 : 0;
+    g.cand_cap = large_cand_cap(n);
+    const int tiles = static_cast<int>((n + kGsTile - 1) / kGsTile);
+    g.below_tile = g.cand + static_cast<size_t>(units) * static_cast<size_t>(g.cand_cap);
+    if (units * tiles > 0x7fffffffLL) return PIC_ERR_TOO_LARGE;
+    gs_pivot_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
+    if (g.vec) gs_sweep_kernel<true, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+    else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+    gs_begin_rounds_kernel<<<static_cast<unsigned>(units), 128, 0, stream>>>(g, w.state, tiles);
+    int rc = launch_status();
+    for (int r = 0; r < 3 && rc == PIC_OK; ++r) {
+        rc = launch_hist_round(std, n, units, r, w.state, w.hist[r], w.min_above, stream,
+                               reinterpret_cast<const float *>(g.cand), g.cand_cap);
+        if (rc == PIC_OK) rc = launch_advance(w.state, w.hist[r], units, r, stream);
+    }
+    if (rc != PIC_OK) return rc;
+    select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
+                                                                                      thr_out, a_out, b_out);
+    return launch_status();
+}
+// picks the sampled select when the workspace allows it (pic_workspace_bytes), else the plain rounds
+static int select_large_or_rounds(const float *std, int64_t n, int64_t units, float q01, const float *q01_per_unit,
+                                  float *thr_out, float *a_out, float *b_out, void *ws, size_t ws_bytes,
+                                  cudaStream_t stream) {
+    static const int sampled = [] { const char *e = getenv("PIC_LARGE_SAMPLED"); return e ? atoi(e) : 1; }();
+    if (sampled && ws_bytes >= large_ws_bytes(n, units))
+        return select_large(std, n, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
+    return select_rounds(std, n, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
 }
 
 static int check_common(int64_t n_per_unit, int64_t units) {
@@ -1386,7 +1442,7 @@ int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *f
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units) {
     if (units <= 0) return 256;
     if (n_per_unit <= kFusedMaxElems) return gs_ws_bytes(units);  // pivots, candidate buffers, thresholds
-    return rounds_ws_bytes(units);
+    return large_ws_bytes(n_per_unit, units);  // rounds state + pivots + candidate buffers (n/8 per unit)
 }
 
 size_t pic_select_state_bytes(int64_t units) { return static_cast<size_t>(units < 1 ? 1 : units) * sizeof(SelectState); }
@@ -1413,7 +1469,7 @@ int pic_select_threshold(const float *std, int64_t n_per_unit, int64_t units, fl
         return launch_fused(p, stream);
     }
     if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
-    return select_rounds(std, n_per_unit, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
+    return select_large_or_rounds(std, n_per_unit, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, ws_bytes, stream);
 }
 
 int pic_select_threshold_multi(const float *std, int64_t n_per_unit, int64_t units, const float *q01_levels,
@@ -1495,7 +1551,8 @@ int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float 
     if (needs_select) {
         if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
         RoundsWs w = carve_ws(ws, units);
-        rc = select_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, stream);
+        rc = select_large_or_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, ws_bytes,
+                                    stream);
         if (rc != PIC_OK) return rc;
         p.thr_in = w.thr;
     }
@@ -1571,7 +1628,8 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
     if (needs_select) {
         if (ws_bytes < rounds_ws_bytes(units) || !ws) return PIC_ERR_WORKSPACE;
         RoundsWs w = carve_ws(ws, units);
-        rc = select_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, stream);
+        rc = select_large_or_rounds(std, n_per_unit, units, q01, q01_per_unit, w.thr, nullptr, nullptr, ws, ws_bytes,
+                                    stream);
         if (rc != PIC_OK) return rc;
         p.thr_in = w.thr;
     }

@@ -20,7 +20,7 @@ namespace pic {
 __device__ constexpr float kNegInvSqrt2 = -0.70710678118654752440f;
 __device__ constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
-enum UnitMode : int { kModeZeros = 0, kModeOnes = 1, kModeThreshold = 2 };
+enum UnitMode : int { kModeZeros = 0, kModeOnes = 1, kModeThreshold = 2, kModeDone = 3 };
 
 __host__ __device__ __forceinline__ int unit_mode(float q01) {
     // sentinels of include/pic_latent.h: q01 < 0 -> ones (pr >= 10), q01 > 1 -> zeros (pr == 0)

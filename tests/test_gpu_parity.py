@@ -550,3 +550,44 @@ def test_elementwise_kernels_vector_and_scalar_paths(pic, dev, n, offset):
         assert_lik_close(N(lik), ref_lik)
     thr = np.array([np.float32(np.median(std))], dtype=np.float32)
     assert np.array_equal(N(pic.ops.mask_from_threshold(D(std), T(thr, dev), 1)), (std >= thr[0]).astype(np.float32))
+
+
+def _select_counters(pic):
+    import ctypes
+    a, b = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    pic.lib().pic_debug_select_counters(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def test_large_unit_sampled_select_and_fallback(pic, dev):
+    """Units above the fused limit: sampled pivots + candidate compaction + histogram rounds over the candidates;
+    tie-heavy / clustered units overflow the candidate buffer and fall back to rounds over the whole unit.  Both
+    branches must be exact, with NaN, +-inf, per-unit q, ones / zeros sentinels in the same call."""
+    rng = np.random.default_rng(77)
+    n = 300003   # not a multiple of 4: scalar sweep
+    rows = [rng.gamma(2.0, 1.0, n).astype(np.float32),                                  # iid: sampled branch
+            np.sort(rng.normal(size=n)).astype(np.float32),                             # sorted
+            np.full(n, 0.25, np.float32),                                               # all equal: overflow -> fallback
+            np.where(rng.random(n) < 0.5, 1.0, 2.0).astype(np.float32),                 # two values
+            (np.round(rng.normal(size=n) * 2) / 2).astype(np.float32),                  # heavy ties
+            np.concatenate([rng.normal(size=n - 2), [np.inf, -np.inf]]).astype(np.float32),
+            np.concatenate([rng.normal(size=n - 1), [np.nan]]).astype(np.float32)]
+    std = np.stack(rows)
+    s0, f0 = _select_counters(pic)
+    for pr in (0.01, 2.5, 5, 7.77, 9.999):
+        thr, a, b = pic.ops.select_threshold(T(std, dev), len(rows), pic.ops.pr_to_q01(pr), want_ab=True)
+        _, rthr = po.channel_mask(std, pr)
+        assert np.array_equal(N(thr), rthr, equal_nan=True), (pr, N(thr), rthr)
+        assert np.all((N(a) <= N(thr)) & (N(thr) <= N(b)) | np.isnan(rthr))
+    s1, f1 = _select_counters(pic)
+    assert s1 > s0 and f1 > f0, "both the sampled branch and the fallback must have run"
+    # per-unit qualities incl. the ones / zeros sentinels, aligned n (vector sweep)
+    n = 1 << 18
+    std = np.stack([rng.gamma(2.0, 1.0, n).astype(np.float32) for _ in range(4)])
+    prs = [0.0, 3.0, 10.0, 6.5]
+    mask, thr = pic.ops.channel_mask(T(std, dev), 4, pic.ops.q01_tensor(prs, dev), want_thr=True)
+    for u, pr in enumerate(prs):
+        rmask, rthr = po.channel_mask(std[u:u + 1], pr)
+        assert np.array_equal(N(mask[u]), rmask[0]), pr
+        if 0 < pr < 10:
+            assert N(thr)[u] == rthr[0]
