@@ -8,6 +8,7 @@
 //                                           full histogram select of the unit by this CTA)
 // Included by pic_latent.cu after the shared helpers (quantile arithmetic, block selects).
 #pragma once
+#include <cooperative_groups.h>
 
 namespace pic {
 
@@ -318,6 +319,152 @@ __global__ void __launch_bounds__(128) gs_begin_rounds_kernel(const GsParams p, 
     st.rank = st.lo;
     st.nan_flag = g.nan_flag;
     state[u] = st;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cluster select: ONE launch replaces the three histogram rounds (+ begin / advance / finish) of a large
+// unit.  A thread-block cluster of 8 CTAs owns one unit: every round each CTA histograms its stripe of the
+// unit's candidate buffer (L2-resident, just written by gs_sweep_kernel) into its own shared memory, the
+// cluster synchronises, and every CTA sums the eight histograms through distributed shared memory and
+// finds the rank's bin redundantly -- no global histograms, no memsets, no kernel boundaries between rounds.
+// Candidate keys are normalised to the bracket, (key - key(plo)) << clz(width), so the 11/11/10-bit digits
+// spread over all bins.  A unit whose bracket missed or overflowed is selected from all of std by the same
+// code (base 0, shift 0): slower, exact.
+// ------------------------------------------------------------------------------------------
+constexpr int kClusterCtas = 8;
+constexpr int kClusterThreads = 1024;
+
+template <bool VEC>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
+gs_cluster_select_kernel(const GsParams p, int tiles_per_unit) {
+    namespace cg = cooperative_groups;
+    constexpr int THREADS = kClusterThreads;
+    constexpr int UNROLL = 4;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) uint32_t hist[2][kHistBins];   // this CTA's histogram, double-buffered across rounds
+    __shared__ __align__(16) uint32_t merged[kHistBins];    // sum over the cluster
+    __shared__ uint32_t scratch[kScratchWords];
+    __shared__ uint32_t red[THREADS / 32];
+    __shared__ uint32_t mn_local;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cluster.block_rank();
+    const int64_t u = blockIdx.y;
+    GsUnit g = p.st[u];
+    if (g.state != 0u) return;   // uniform over the cluster: ones / zeros / tiny unit, done by gs_pivot_kernel
+    if (p.below_tile) {          // per-tile counts below the bracket -> c_below
+        uint32_t acc = 0;
+        for (int t = tid; t < tiles_per_unit; t += THREADS) acc += p.below_tile[u * tiles_per_unit + t];
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        acc = (lane < THREADS / 32) ? red[lane] : 0u;
+        g.c_below = __reduce_add_sync(0xffffffffu, acc);
+    }
+    const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
+    uint32_t lo, hi;
+    float w;
+    quantile_ranks(q, p.n, lo, hi, w);
+    const bool valid = g.c_cand <= static_cast<uint32_t>(p.cand_cap) && g.c_below <= lo && hi < g.c_below + g.c_cand;
+    const float *src = p.std + u * p.n;
+    int64_t len = p.n;
+    uint32_t base = 0u;
+    int lsh = 0;
+    bool vec = VEC;
+    if (valid) {
+        src = reinterpret_cast<const float *>(p.cand) + u * p.cand_cap;   // 16-byte aligned: cand_cap % 4 == 0
+        len = g.c_cand;
+        lo -= g.c_below;
+        hi -= g.c_below;
+        base = float_to_key(g.plo_f);
+        lsh = __clz((float_to_key(g.phi_f) - base) | 1u);
+        vec = true;
+    }
+    if (tid == 0 && crank == 0) atomicAdd(valid ? &g_sampled_units : &g_fallback_units, 1ull);
+    const int64_t nvec = vec ? (len >> 2) : 0;
+    const int64_t v0 = nvec * crank / kClusterCtas, v1 = nvec * (crank + 1) / kClusterCtas;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    uint32_t prefix = 0, rank = lo, below_total = 0, count = 0, mn = 0xffffffffu, last_bin = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        constexpr int kUp[3] = {32, 21, 10};   // bits above round r's digit
+        const int shift = round_shift(r), nbins = round_bins(r), up = kUp[r];
+        uint32_t *h = hist[r & 1];
+        for (int j = tid; j < nbins; j += THREADS) h[j] = 0u;
+        __syncthreads();
+        const uint32_t want = (r > 0) ? (prefix >> up) : 0u;
+        auto visit = [&](float x, bool inb) {
+            const uint32_t k = (float_to_key(x) - base) << lsh;
+            bool match = inb;
+            if (r > 0) {
+                const uint32_t hb = k >> up;
+                if (r == 2 && inb && hb > want) mn = min(mn, k);
+                match = inb && hb == want;
+            }
+            hist_add(h, (k >> shift) & round_mask(r), match);
+        };
+        for (int64_t jb = v0 + (tid - lane) * UNROLL; jb < v1; jb += THREADS * UNROLL) {
+            float4 v[UNROLL];
+            bool inb[UNROLL];
+#pragma unroll
+            for (int i = 0; i < UNROLL; ++i) {
+                const int64_t j = jb + i * 32 + lane;
+                inb[i] = j < v1;
+                v[i] = inb[i] ? __ldg(s4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < UNROLL; ++i) {
+                visit(v[i].x, inb[i]); visit(v[i].y, inb[i]); visit(v[i].z, inb[i]); visit(v[i].w, inb[i]);
+            }
+        }
+        // scalar remainder (everything when the source is not float4-addressable), striped over the cluster
+        const int64_t t0 = nvec << 2, tn = len - t0;
+        const int64_t e0 = t0 + tn * crank / kClusterCtas, e1 = t0 + tn * (crank + 1) / kClusterCtas;
+        for (int64_t jb = e0 + tid - lane; jb < e1; jb += THREADS) {
+            const int64_t j = jb + lane;
+            const bool inb = j < e1;
+            visit(inb ? __ldg(src + j) : 0.0f, inb);
+        }
+        if (r == 2) {
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            if (tid == 0) mn_local = 0xffffffffu;
+            __syncthreads();
+            if (lane == 0 && mn != 0xffffffffu) atomicMin(&mn_local, mn);
+        }
+        __syncthreads();
+        cluster.sync();   // every CTA's histogram of this round is complete and visible
+        for (int j = tid; j < nbins; j += THREADS) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int c = 0; c < kClusterCtas; ++c) sum += cluster.map_shared_rank(h, c)[j];
+            merged[j] = sum;
+        }
+        __syncthreads();
+        const BinHit hit = block_find_bin<THREADS>(merged, nbins, rank, scratch);
+        prefix |= hit.bin << shift;
+        rank -= hit.below;
+        below_total += hit.below;
+        count = hit.count;
+        last_bin = hit.bin;
+    }
+    uint32_t a_key = prefix, b_key = prefix;
+    if (!(hi < below_total + count)) {
+        const uint32_t nb = block_next_nonempty<THREADS>(merged, round_bins(2), last_bin, scratch);
+        if (nb != 0xffffffffu) {
+            b_key = (prefix & ~round_mask(2)) | nb;
+        } else {          // next key lies beyond the last digit's range: smallest key above, over the cluster
+            uint32_t m = 0xffffffffu;
+            for (int c = 0; c < kClusterCtas; ++c) m = min(m, *cluster.map_shared_rank(&mn_local, c));
+            b_key = m;
+        }
+    }
+    cluster.sync();       // no CTA may exit while a peer still reads its shared memory
+    if (crank != 0 || tid != 0) return;
+    float a = key_to_float((a_key >> lsh) + base), b = key_to_float((b_key >> lsh) + base);
+    float t = quantile_lerp(a, b, w);
+    if (g.nan_flag) t = a = b = __int_as_float(0x7fc00000);
+    p.thr[u] = t;
+    if (p.a_out) p.a_out[u] = a;
+    if (p.b_out) p.b_out[u] = b;
 }
 
 }  // namespace pic

@@ -1347,6 +1347,13 @@ static int select_large(const float *std, int64_t n, int64_t units, float q01, c
     gs_pivot_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
     if (g.vec) gs_sweep_kernel<true, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
     else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
+    static const int use_cluster = [] { const char *e = getenv("PIC_CLUSTER_SELECT"); return e ? atoi(e) : 1; }();
+    if (use_cluster && units <= 65535) {
+        const dim3 grid(kClusterCtas, static_cast<unsigned>(units));
+        if (g.vec) gs_cluster_select_kernel<true><<<grid, kClusterThreads, 0, stream>>>(g, tiles);
+        else gs_cluster_select_kernel<false><<<grid, kClusterThreads, 0, stream>>>(g, tiles);
+        return launch_status();
+    }
     gs_begin_rounds_kernel<<<static_cast<unsigned>(units), 128, 0, stream>>>(g, w.state, tiles);
     int rc = launch_status();
     for (int r = 0; r < 3 && rc == PIC_OK; ++r) {
