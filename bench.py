@@ -73,18 +73,20 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi samples of every GPU of the job during the timed region (rank 0 runs it)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, n_gpus: int = 1):
+        self.ids = [index] if n_gpus <= 1 else list(range(n_gpus))
+        self.rows, self.proc = [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "--id=" + ",".join(map(str, self.ids)), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
@@ -99,25 +101,29 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
         self.proc.terminate()
-        allsm, sm, smax, reasons = [], [], [], set()
+        inside, anytime, smax, reasons = {}, {}, [], set()
         for ts, line in self.rows:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                clk, mx = float(parts[0]), float(parts[1])
+                gpu, clk, mx = int(parts[0]), float(parts[1]), float(parts[2])
             except ValueError:
                 continue
             smax.append(mx)
-            allsm.append(clk)
+            anytime.setdefault(gpu, []).append(clk)
             if t0 <= ts <= t1 + 0.03:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                inside.setdefault(gpu, []).append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        use = sm if sm else allsm
-        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples_in_timed_region": len(sm)}
+        use = inside if inside else anytime
+        med = {g: statistics.median(v) for g, v in use.items() if v}
+        out = {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(smax) if smax else None,
+               "reasons": sorted(reasons), "samples_in_timed_region": min((len(v) for v in inside.values()), default=0)}
+        if len(self.ids) > 1:
+            out["sm_mhz_by_gpu"] = [med.get(g) for g in self.ids]   # sm_mhz is the slowest GPU's median
+        return out
 
 
 # ------------------------------------------------------------------------------------------ inputs
@@ -375,7 +381,31 @@ def run_cuda(args, wl):
     for _ in range(warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    # The timed steps replay ONE step captured in a CUDA graph (the launch-bound loop: 2 launches / 0.3 ms), so that
+    # host scheduling of N processes on one box does not leak into a device measurement; the same K steps issued
+    # eagerly are timed first and reported as eager_ms_per_step.  NCCL steps (tiled, N > 1) stay eager.
+    run_step, eager_ms = step, None
+    use_graph = bool(args.graph) and not (name == "tile8192" and world > 1)
+    if use_graph:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            step()
+        g1.record()
+        barrier()
+        eager_ms = g0.elapsed_time(g1) / args.steps
+        if world > 1:
+            t = torch.tensor([eager_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            eager_ms = float(t.item())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(3):
+            graph.replay()
+        run_step = graph.replay
+        barrier()
+    sampler = ClockSampler(local_rank, world)
     if rank == 0:
         sampler.start()
         time.sleep(0.1)
@@ -384,14 +414,18 @@ def run_cuda(args, wl):
     t_wall0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        step()
+        run_step()
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
+    rank_ms = [ms / args.steps]
     if world > 1:
         tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        every = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(every, tms)
+        rank_ms = [float(t.item()) / args.steps for t in every]     # reported for transparency
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)                  # the step time is the slowest rank's
         ms = float(tms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = ms / args.steps
@@ -513,9 +547,11 @@ def run_cuda(args, wl):
     line = {
         "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic", "ms_per_step_by_rank": [round(t, 5) for t in rank_ms],
+        "eager_ms_per_step": eager_ms,
         "config": {"workload": name, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
                    "units_per_step_per_gpu": units, "elements_per_step": total_elems, "launch": args.launch,
+                   "cuda_graph": use_graph,
                    "launches_per_step": launches[0], "outputs": list(want), "bytes_per_elem": wl["bytes_per_elem"],
                    "l2": f"inputs of one step = {elems_per_rank * 16 / 1e6:.0f} MB per GPU > 126 MB L2, no explicit flush",
                    "parallelism": (f"{world} rank(s), row-band tiles + NCCL histogram all-reduce" if name == "tile8192"
@@ -536,6 +572,7 @@ def main():
     ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
                     help="kodak_sweep: all (slice, q) units of a step in one launch, or one launch per slice index")
+    ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -88,8 +88,11 @@ __global__ void __launch_bounds__(kGsThreads, 5) gs_pivot_kernel(const GsParams 
         return;
     }
     // sample (hashed stride) -> cand
-    int S = n >> 3;
-    S = S < 1024 ? 1024 : (S > kCandMax ? kCandMax : S);
+    // fused-size units: bracket (~8 % at S = 2048) must fit the kCandMax finish buffer; large units: the
+    // largest sample the pivot CTA holds, for the narrowest bracket (~6 % of the unit)
+    const int s_max = (p.cand_cap == kCandMax) ? kSampleMax : kCandMax;
+    int S = (p.cand_cap == kCandMax) ? (n >> 4) : (n >> 3);
+    S = S < 1024 ? 1024 : (S > s_max ? s_max : S);
     S &= ~3;
     if (p.vec) {
         const int nvec = n >> 2, S4 = S >> 2;
