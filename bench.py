@@ -302,7 +302,7 @@ def run_cuda(args, wl):
         def step():
             if world == 1:
                 ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
-                launches[0] = 9          # begin + 3 x (hist, advance) + finish + apply (+ 4 memsets, not kernels)
+                launches[0] = plan(n, units)[1]   # pivot + sweep + cluster select + apply = 4
             else:
                 thr = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
                 ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr, want=want, out=outs)
@@ -339,12 +339,10 @@ def run_cuda(args, wl):
         main_kernel = PLAN_KERNEL[fwd_kind]
 
         def step():
-            star = ops.channel_mask(std_pre, units, q_all)               # pre-REM attention mask
-            att[:, 0].copy_(star)
-            att[:, 1].copy_(star)                                        # cat([m, m], 1) for mu_std
+            ops.attention_mask(std_pre, units, q_all, copies=2, out=att)  # pre-REM star mask, cat([m, m], 1)
             ops.select_threshold(std_pre, units, ops.pr_to_q01(0.75))    # checkpoint pass threshold
             ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs)
-            launches[0] = 2 + fwd_k                                      # ours; the two copies are torch's
+            launches[0] = 3 + fwd_k                                      # select + mask pass, select, slice
         elems_per_rank = units * n
         total_elems = elems_per_rank * world
     else:

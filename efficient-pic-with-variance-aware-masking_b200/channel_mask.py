@@ -117,6 +117,9 @@ class ChannelMask(nn.Module):
         """models/rem_pic.py:181-195 (apply_latent_enhancement): the `star_mask` at quality `pr` on the
         pre-REM scale, rounded, duplicated on the channel axis when the REM refines (mu, std) jointly.
         (The reference also computes a `bar_mask` at `quality_bar` and discards it; not reproduced.)"""
+        if mu_std and mask_pol == "point-based-std" and scale.dim() >= 2:
+            # one select + one pass writes both halves; apply_noise is the identity on a {0,1} mask without grad
+            return ops.attention_mask(scale.contiguous(), scale.shape[0], ops.pr_to_q01(pr), copies=2)
         m = self.apply_noise(self.forward(scale, pr=pr, mask_pol=mask_pol), training)
         return torch.cat([m, m], dim=1) if mu_std else m
 

@@ -1018,24 +1018,35 @@ __global__ void __launch_bounds__(256) dequantize_kernel(const int32_t *symbols,
     }
 }
 
-// vec: n_per_unit % 4 == 0 and aligned pointers, so a float4 never straddles two units
+// vec: n_per_unit % 4 == 0 and aligned pointers, so a float4 never straddles two units.
+// copies > 1: output layout [units][copies][n_per_unit] -- the REM attention mask cat([m, m], 1)
+// (models/rem_pic.py:181-195) written once instead of mask + two copies.
 __global__ void __launch_bounds__(256) mask_from_threshold_kernel(const float *std, const float *thr,
                                                                   int64_t n_per_unit, int64_t total,
-                                                                  float *mask, bool vec) {
+                                                                  float *mask, bool vec, int copies, float q01,
+                                                                  const float *q01_per_unit) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (vec) {
         for (int64_t j = t0; j < (total >> 2); j += stride) {
-            const float t = __ldg(thr + (4 * j) / n_per_unit);
+            const int64_t u = (4 * j) / n_per_unit;
+            const int mode = unit_mode(q01_per_unit ? __ldg(q01_per_unit + u) : q01);   // ones / zeros ignore std
+            const float t = __ldg(thr + u);
             const float4 s = __ldg(reinterpret_cast<const float4 *>(std) + j);
-            reinterpret_cast<float4 *>(mask)[j] = make_float4((s.x >= t) ? 1.0f : 0.0f, (s.y >= t) ? 1.0f : 0.0f,
-                                                              (s.z >= t) ? 1.0f : 0.0f, (s.w >= t) ? 1.0f : 0.0f);
+            float4 m = make_float4((s.x >= t) ? 1.0f : 0.0f, (s.y >= t) ? 1.0f : 0.0f,
+                                   (s.z >= t) ? 1.0f : 0.0f, (s.w >= t) ? 1.0f : 0.0f);
+            if (mode != kModeThreshold) m.x = m.y = m.z = m.w = (mode == kModeOnes) ? 1.0f : 0.0f;
+            float *dst = mask + 4 * j + u * (copies - 1) * n_per_unit;
+            for (int c = 0; c < copies; ++c) *reinterpret_cast<float4 *>(dst + c * n_per_unit) = m;
         }
         return;
     }
     for (int64_t j = t0; j < total; j += stride) {
-        const float t = thr[j / n_per_unit];
-        mask[j] = (std[j] >= t) ? 1.0f : 0.0f;
+        const int64_t u = j / n_per_unit;
+        const int mode = unit_mode(q01_per_unit ? q01_per_unit[u] : q01);
+        const float m = (mode != kModeThreshold) ? ((mode == kModeOnes) ? 1.0f : 0.0f) : ((std[j] >= thr[u]) ? 1.0f : 0.0f);
+        float *dst = mask + j + u * (copies - 1) * n_per_unit;
+        for (int c = 0; c < copies; ++c) dst[c * n_per_unit] = m;
     }
 }
 
@@ -1320,6 +1331,16 @@ static int select_rounds(const float *std, int64_t n, int64_t units, float q01, 
     return launch_status();
 }
 
+// debugging switches of the large-unit select (defaults: sampled sweep + cluster select)
+static int env_large_sampled() {
+    static const int v = [] { const char *e = getenv("PIC_LARGE_SAMPLED"); return e ? atoi(e) : 1; }();
+    return v;
+}
+static int env_cluster_select() {
+    static const int v = [] { const char *e = getenv("PIC_CLUSTER_SELECT"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
 // Large units (> kFusedMaxElems) on one device: sampled pivots -> one tile-ordered sweep that counts the
 // elements below the bracket and compacts the bracket (~6 % of the unit) into a candidate buffer -> the three
 // histogram rounds over the candidates only.  Units whose bracket missed or overflowed run the same rounds over
@@ -1347,8 +1368,7 @@ static int select_large(const float *std, int64_t n, int64_t units, float q01, c
     gs_pivot_kernel<<<static_cast<unsigned>(units), kGsThreads, 0, stream>>>(g);
     if (g.vec) gs_sweep_kernel<true, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
     else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * tiles), kGsThreads, 0, stream>>>(g, tiles);
-    static const int use_cluster = [] { const char *e = getenv("PIC_CLUSTER_SELECT"); return e ? atoi(e) : 1; }();
-    if (use_cluster && units <= 65535) {
+    if (env_cluster_select() && units <= 65535) {
         const dim3 grid(kClusterCtas, static_cast<unsigned>(units));
         if (g.vec) gs_cluster_select_kernel<true><<<grid, kClusterThreads, 0, stream>>>(g, tiles);
         else gs_cluster_select_kernel<false><<<grid, kClusterThreads, 0, stream>>>(g, tiles);
@@ -1370,8 +1390,7 @@ static int select_large(const float *std, int64_t n, int64_t units, float q01, c
 static int select_large_or_rounds(const float *std, int64_t n, int64_t units, float q01, const float *q01_per_unit,
                                   float *thr_out, float *a_out, float *b_out, void *ws, size_t ws_bytes,
                                   cudaStream_t stream) {
-    static const int sampled = [] { const char *e = getenv("PIC_LARGE_SAMPLED"); return e ? atoi(e) : 1; }();
-    if (sampled && ws_bytes >= large_ws_bytes(n, units))
+    if (env_large_sampled() && ws_bytes >= large_ws_bytes(n, units))
         return select_large(std, n, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
     return select_rounds(std, n, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
 }
@@ -1421,7 +1440,9 @@ int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, 
     static const int two_kernel = [] { const char *e = getenv("PIC_TWO_KERNEL"); return e ? atoi(e) : 1; }();
     static const int gsel = [] { const char *e = getenv("PIC_GLOBAL_SELECT"); return e ? atoi(e) : 0; }();
     if (n_per_unit > kFusedMaxElems) {
-        *n_kernels = needs_select ? 9 : 1;   // begin + 3 x (hist, advance) + finish + apply
+        // with the full workspace: pivot + sweep + cluster select + apply; plain rounds: begin + 3 x (hist,
+        // advance) + finish + apply
+        *n_kernels = !needs_select ? 1 : (!env_large_sampled() ? 9 : (env_cluster_select() && units <= 65535 ? 4 : 11));
         return 2;
     }
     if (two_kernel && (!needs_select || n_per_unit >= kTwoKernelMinUnit)) {
@@ -1566,13 +1587,33 @@ int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float 
     return launch_apply(p, stream);
 }
 
+int pic_attention_mask(const float *std, int64_t n_per_unit, int64_t units, float q01, const float *q01_per_unit,
+                       int copies, float *mask, float *thr_out, void *ws, size_t ws_bytes, pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!std || !mask || copies < 1 || copies > 8) return PIC_ERR_INVALID_ARGUMENT;
+    if (!aligned4(std) || !aligned4(mask)) return PIC_ERR_UNALIGNED;
+    if (copies == 1) return pic_channel_mask(std, n_per_unit, units, q01, q01_per_unit, mask, thr_out, ws, ws_bytes, stream_);
+    if (!ws || ws_bytes < pic_workspace_bytes(n_per_unit, units)) return PIC_ERR_WORKSPACE;
+    // thresholds (select only; ones / zeros sentinels give -inf / +inf), then one pass writes every copy
+    float *thr = thr_out;
+    if (!thr) thr = (n_per_unit <= kFusedMaxElems) ? gs_thr_buffer(ws, units) : carve_ws(ws, units).thr;
+    rc = pic_select_threshold(std, n_per_unit, units, q01, q01_per_unit, thr, nullptr, nullptr, ws, ws_bytes, stream_);
+    if (rc != PIC_OK) return rc;
+    const int64_t total = n_per_unit * units;
+    const bool vec = (n_per_unit % 4 == 0) && aligned16(std) && aligned16(mask);
+    mask_from_threshold_kernel<<<elementwise_grid(total, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        std, thr, n_per_unit, total, mask, vec, copies, q01, q01_per_unit);
+    return launch_status();
+}
+
 int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_unit, int64_t units, float *mask,
                             pic_stream_t stream_) {
     if (n_per_unit <= 0 || units <= 0 || !std || !thr || !mask) return PIC_ERR_INVALID_ARGUMENT;
     const int64_t total = n_per_unit * units;
     const bool vec = (n_per_unit % 4 == 0) && aligned16(std) && aligned16(mask);
     mask_from_threshold_kernel<<<elementwise_grid(total, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        std, thr, n_per_unit, total, mask, vec);
+        std, thr, n_per_unit, total, mask, vec, 1, 0.5f, nullptr);
     return launch_status();
 }
 

@@ -121,6 +121,23 @@ def channel_mask(std: torch.Tensor, units: int, q01, want_thr: bool = False):
     return (mask, thr) if want_thr else mask
 
 
+def attention_mask(std: torch.Tensor, units: int, q01, copies: int = 2, out: Optional[torch.Tensor] = None):
+    """REM attention mask: channel_mask written `copies` times along dim 1, shape [units, copies * C, ...]
+    (torch.cat([m] * copies, 1) of the reference) from one select + one pass over std."""
+    std = _require(std, "std")
+    units, n = _units_view(std, units)
+    q, qt = _q_args(q01, units, std.device)
+    if out is None:
+        shape = (units, copies * n) if std.dim() < 2 else (std.shape[0], copies * std.shape[1]) + tuple(std.shape[2:])
+        out = torch.empty(shape, dtype=torch.float32, device=std.device)
+    elif out.numel() != units * copies * n or not out.is_contiguous():
+        raise ValueError("out must be a contiguous tensor of units * copies * n elements")
+    ws, ws_bytes = _workspace(n, units, std.device)
+    check(lib().pic_attention_mask(_ptr(std), n, units, q, _ptr(qt), copies, _ptr(out), None, _ptr(ws), ws_bytes,
+                                   _stream()), "pic_attention_mask")
+    return out
+
+
 def select_threshold_multi(std: torch.Tensor, units: int, prs: Sequence[Number]) -> torch.Tensor:
     """Thresholds of every unit at every quality of `prs` in one launch. Returns thr [units, len(prs)]."""
     std = _require(std, "std")

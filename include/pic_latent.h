@@ -67,15 +67,20 @@ int pic_last_cuda_error(void); /* cudaError_t of the last failing runtime call o
 int64_t pic_fused_max_elems(void);
 
 /* Launch plan of pic_slice_forward for a problem size: returns 0 (single fused kernel), 1 (select
- * kernel + tile-ordered apply kernel) or 2 (multi-launch radix rounds + apply kernel) and stores the
- * number of kernel launches in *n_kernels.  needs_select = 0 when thresholds are supplied. */
+ * kernel + tile-ordered apply kernel) or 2 (large units: pivot + sweep + cluster select + apply kernel, given
+ * the workspace of pic_workspace_bytes) and stores the number of kernel launches in *n_kernels.  needs_select = 0 when thresholds are supplied. */
 int pic_slice_forward_plan(int64_t n_per_unit, int64_t units, int needs_select, int *n_kernels);
 
 /* Diagnostics (synchronises the device): number of units served by the sampled-pivot select and
  * number that fell back to the full histogram select, since the library was loaded. */
 int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *fallback);
 
-/* Scratch needed by pic_select_threshold / pic_channel_mask / pic_slice_forward. */
+/* Scratch needed by pic_select_threshold / pic_channel_mask / pic_slice_forward (caller-owned device memory,
+ * reusable across calls on the same stream).  Units up to pic_fused_max_elems(): ~20 KB per unit (pivots,
+ * candidates, thresholds).  Larger units: round state + histograms + a candidate buffer of n_per_unit / 8 floats
+ * and one counter per 8192 elements per unit (sampled sweep + cluster select).  A smaller workspace is accepted
+ * for large units down to the plain radix rounds' need (~25 KB per unit) and selects that slower path;
+ * below that the call returns PIC_ERR_WORKSPACE. */
 size_t pic_workspace_bytes(int64_t n_per_unit, int64_t units);
 
 /*
@@ -131,6 +136,16 @@ int pic_select_finish(const void *state, const uint32_t *min_above, int64_t unit
 int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float q01,
                      const float *q01_per_unit, float *mask, float *thr_out, void *ws,
                      size_t ws_bytes, pic_stream_t stream);
+
+/*
+ * REM attention mask (models/rem_pic.py:181-195; consumed at layers/rem.py:137-140): the star mask of
+ * pic_channel_mask written `copies` times along the channel axis, out = [units][copies][n_per_unit]
+ * (copies = 2 is torch.cat([m, m], 1) for the joint (mu, std) refinement; copies = 1 is pic_channel_mask).
+ * One select + one pass over std instead of mask + `copies` tensor copies.  thr_out nullable.
+ */
+int pic_attention_mask(const float *std, int64_t n_per_unit, int64_t units, float q01,
+                       const float *q01_per_unit, int copies, float *mask, float *thr_out, void *ws,
+                       size_t ws_bytes, pic_stream_t stream);
 
 /* mask = (std >= thr[u]) with thresholds already known (e.g. all-reduced ones). */
 int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_unit,

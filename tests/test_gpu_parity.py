@@ -446,6 +446,20 @@ def test_rem_attention_mask_and_rate(pic, dev):
     ref, _ = po.channel_mask(std.reshape(2, -1), 0.75)
     assert att.shape == (2, 64, 8, 8)
     assert np.array_equal(N(att[:, :32]), ref.reshape(2, 32, 8, 8)) and torch.equal(att[:, :32], att[:, 32:])
+    # sentinels (pr >= 10 -> ones, pr == 0 -> zeros) ignore std even where it is NaN / +inf; per-unit qualities;
+    # a large unit (workspace path); an odd element count (scalar path); 3 copies
+    std[0, 0, 0, :4] = [np.nan, np.inf, -np.inf, 0.0]
+    s = T(std, dev)
+    assert torch.equal(masking.attention_mask(s, 10, mu_std=True), torch.ones(2, 64, 8, 8, device=dev))
+    assert torch.equal(masking.attention_mask(s, 0, mu_std=True), torch.zeros(2, 64, 8, 8, device=dev))
+    big = trained_like(rng, (3, 140001))[3]
+    prs = [10.0, 3.3, 0.0]
+    got = pic.ops.attention_mask(T(big, dev), 3, pic.ops.q01_tensor(prs, dev), copies=3)
+    assert got.shape == (3, 3 * 140001)
+    for u, pr in enumerate(prs):
+        want_u, _ = po.channel_mask(big[u:u + 1], pr)
+        for c in range(3):
+            assert np.array_equal(N(got[u, c * 140001:(c + 1) * 140001]), want_u[0]), (u, c)
     lik = torch.rand(3, 32, 16, 16, device=dev) * 0.9 + 0.05
     bpp = pic.rate_bpp(lik, num_pixels=3 * 256 * 256)
     want = float(torch.log(lik.double()).sum() / (-np.log(2) * 3 * 256 * 256))
