@@ -14,9 +14,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libpic_latent.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu", "pic_rans.cpp")]
 _HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh")] + [
-    os.path.join(_ROOT, "include", "pic_latent.h")]
+    os.path.join(_ROOT, "include", "pic_latent.h"), os.path.join(_ROOT, "include", "pic_codec.h")]
 
 PIC_OK = 0
 PIC_ERR_INVALID_ARGUMENT = -1
@@ -29,9 +29,10 @@ Q_ONES = -1.0
 Q_ZEROS = 2.0
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+_tables = [_vp, _i32, _i32, _vp, _vp]   # cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets (include/pic_codec.h)
 
 # name -> (restype, argtypes); must list every symbol of include/pic_latent.h
 SIGNATURES = {
@@ -65,6 +66,13 @@ SIGNATURES = {
     "pic_quantize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pic_dequantize": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pic_log_sum": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    # include/pic_codec.h (host code: CDF tables + rANS)
+    "pic_pmf_to_quantized_cdf": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "pic_rans_stream_bound": (_i64, [_i64]),
+    "pic_rans_encode_with_indexes": (_i64, [_vp, _vp, _i64] + _tables + [_vp, _i64]),
+    "pic_rans_decode_with_indexes": (C.c_int, [_vp, _i64, _vp, _i64] + _tables + [_vp]),
+    "pic_rans_encode_batch": (C.c_int, [_vp, _vp, _i64, _i64] + _tables + [_vp, _i64, _vp, _i32]),
+    "pic_rans_decode_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64] + _tables + [_vp, _i32]),
     "pic_host_pipeline_bytes": (_sz, [_i64, _i64]),
     "pic_slice_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _f32, _f32,
                                          _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),

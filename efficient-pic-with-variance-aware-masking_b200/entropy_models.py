@@ -9,9 +9,10 @@ libpic_latent.so with a fused backward.
 
 Reference lines: EntropyModel 70-168 (quantize 127-153, dequantize 161-168),
 GaussianConditional 528-672 (_likelihood 620-635, forward 637-652, build_indexes 654-659).
-Out of scope here ("next"): rANS compress/decompress (206-294) and the CDF-table
-build in update() (591-618) need compressai's C++ extension; they delegate to compressai when
-it is importable and raise otherwise.  EntropyBottleneck (297-525) is not on the path.
+Codec side: rANS compress/decompress (206-294) and the CDF-table build in
+update() (591-618) use compressai's C++ extension when it is importable, else the native coder of
+this package (codec.py over include/pic_codec.h: same bit-stream by construction, byte parity with
+compressai unpinned because it is not installed here).  EntropyBottleneck (297-525) is not on the path.
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from . import ops
+from . import codec, ops
 
 
 class _LowerBoundFn(torch.autograd.Function):
@@ -96,7 +97,9 @@ def _make_entropy_coder(method):
             method = get_entropy_coder()
         return _EntropyCoder(method)
     except ImportError:
-        return None  # compressai absent: compress()/decompress() raise, the latent path is unaffected
+        if method not in (None, "ans"):
+            raise ValueError(f'Unknown entropy coder "{method}" (available: ans)')
+        return codec.RansCoder()  # compressai absent: the native rANS coder of this package
 
 
 class EntropyModel(nn.Module):
@@ -158,15 +161,43 @@ class EntropyModel(nn.Module):
         warnings.warn("_dequantize. Use dequantize instead.")
         return cls.dequantize(inputs, means)
 
-    # ---- rANS coding (206-294): out of scope, delegates to compressai -----------------------
+    # ---- rANS coding (206-294) ----------------------------------------------------------
+    def _check_cdf_size(self):
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+
+    def _check_offsets_size(self):
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if len(self._offset.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+
+    def _check_cdf_length(self):
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if len(self._cdf_length.size()) != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+
+    def _tables(self) -> "codec.CdfTables":
+        """Host copy of the CDF tables for the native coder, rebuilt when update() replaces the buffers."""
+        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, self._quantized_cdf.numel())
+        if getattr(self, "_tables_key", None) != key:
+            self._check_cdf_size(), self._check_cdf_length(), self._check_offsets_size()
+            self._tables_cache = codec.CdfTables(self._quantized_cdf, self._cdf_length, self._offset)
+            self._tables_key = key
+        return self._tables_cache
+
     def compress(self, inputs, indexes, means=None, flag=1, already_quantize=False):
-        if self.entropy_coder is None:
-            raise RuntimeError("compress() needs compressai's rANS coder, which is not installed")
         symbols = self.quantize(inputs, "symbols", means) if already_quantize is False else inputs
         if len(inputs.size()) < 2:
             raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
         if symbols.size() != indexes.size():
             raise ValueError("`inputs` and `indexes` should have the same size.")
+        if isinstance(self.entropy_coder, codec.RansCoder):
+            # one D2H copy of the int32 symbols / indexes, every stream (dim 0) on its own host thread
+            return codec.encode_streams(symbols, indexes, self._tables())
         strings = []
         for i in range(symbols.size(0)):
             rv = self.entropy_coder.encode_with_indexes(
@@ -177,15 +208,24 @@ class EntropyModel(nn.Module):
         return strings
 
     def decompress(self, strings, indexes, means=None, flag=1):
-        if self.entropy_coder is None:
-            raise RuntimeError("decompress() needs compressai's rANS coder, which is not installed")
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if not len(strings) == indexes.size(0):
             raise ValueError("Invalid strings or indexes parameters")
         if len(indexes.size()) < 2:
             raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_cdf_size(), self._check_cdf_length(), self._check_offsets_size()
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, len(indexes.size())):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
         cdf = self._quantized_cdf
+        if isinstance(self.entropy_coder, codec.RansCoder):
+            outputs = codec.decode_streams(strings, indexes, self._tables()).to(indexes.device)
+            return self.dequantize(outputs, means)
         outputs = cdf.new_empty(indexes.size())
         for i, s in enumerate(strings):
             values = self.entropy_coder.decode_with_indexes(
@@ -273,15 +313,14 @@ class GaussianConditional(EntropyModel):
         return True
 
     def update(self, scale_table):
-        """entropy_models.py:591-618.  The scale table is installed unconditionally (that is all the
-        latent path needs); the quantised-CDF build needs compressai's C++ pmf_to_quantized_cdf."""
+        """entropy_models.py:591-618: the pmf with the reference's own torch ops (f32, on the host: 64 rows), the
+        16-bit CDF rows through compressai's pmf_to_quantized_cdf when importable, else pic_pmf_to_quantized_cdf."""
         device = self.scale_table.device
         self.scale_table = self._prepare_scale_table(scale_table).to(device)
         try:
             from compressai._CXX import pmf_to_quantized_cdf as _pmf_to_quantized_cdf
         except ImportError:
-            warnings.warn("compressai is not installed: scale_table updated, CDF tables left untouched")
-            return
+            _pmf_to_quantized_cdf = codec.pmf_to_quantized_cdf
         table = self.scale_table.cpu()
         multiplier = -self._standardized_quantile(self.tail_mass / 2)
         pmf_center = torch.ceil(table * multiplier).int()

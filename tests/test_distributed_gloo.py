@@ -59,7 +59,7 @@ def test_tiled_select_two_ranks_gloo():
     po.build()
     units, n = 6, 6000
     prs = [0.5, 5, 9.9999, 0, 10, 1e-4]
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()   # no fork() of a process that has run host threads
     ret = mgr.dict()
     port = _free_port()
     mp.spawn(_worker, args=(2, port, units, n, prs, ret), nprocs=2, join=True)

@@ -20,7 +20,8 @@ def _built():
 
 
 def header_symbols():
-    text = open(os.path.join(ROOT, "include", "pic_latent.h")).read()
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include")))
+                   if h.endswith(".h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(pic_[a-z0-9_]+)\s*\(", text)))
 
@@ -30,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 24
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
-        assert hasattr(handle, s), f"{s} declared in include/pic_latent.h but not exported"
+        assert hasattr(handle, s), f"{s} declared in include/*.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "python binding table out of sync with the header"
 
 
