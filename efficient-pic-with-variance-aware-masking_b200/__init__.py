@@ -5,7 +5,8 @@ Public surface = the reference's own API for this path (drop-in):
     EntropyModel, GaussianConditional           (entropy_models/entropy_models.py)
     get_scale_table                             (models/pic.py:12-17)
 plus the fused per-slice operator ``progressive_slice_forward`` and the spatially tiled
-multi-GPU select (``distributed``).  All compute runs in libpic_latent.so (hand-written
+multi-GPU select (``distributed``), and the host-side coder after the path (``codec``: CDF tables,
+rANS streams, progressive level packing; include/pic_codec.h).  All compute runs in libpic_latent.so (hand-written
 sm_100a CUDA behind the C ABI of include/pic_latent.h); importing this package never builds
 or falls back: a missing library raises at first use.
 """
@@ -13,7 +14,7 @@ import math
 
 import torch
 
-from . import _lib, distributed, ops
+from . import _lib, codec, distributed, ops
 from ._lib import LIB_PATH, build, lib
 from .channel_mask import ChannelMask, ste_round
 from .entropy_models import EntropyModel, GaussianConditional, LowerBound
@@ -30,4 +31,4 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
 
 
 __all__ = ["ChannelMask", "ste_round", "EntropyModel", "GaussianConditional", "LowerBound",
-           "progressive_slice_forward", "rate_bpp", "get_scale_table", "ops", "distributed", "build", "lib", "LIB_PATH"]
+           "progressive_slice_forward", "rate_bpp", "get_scale_table", "ops", "codec", "distributed", "build", "lib", "LIB_PATH"]

@@ -73,6 +73,8 @@ SIGNATURES = {
     "pic_rans_decode_with_indexes": (C.c_int, [_vp, _i64, _vp, _i64] + _tables + [_vp]),
     "pic_rans_encode_batch": (C.c_int, [_vp, _vp, _i64, _i64] + _tables + [_vp, _i64, _vp, _i32]),
     "pic_rans_decode_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64] + _tables + [_vp, _i32]),
+    "pic_rans_encode_levels": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32] + _tables + [_vp, _i64, _vp, _i32]),
+    "pic_rans_decode_levels": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32] + _tables + [_vp, _i32]),
     "pic_host_pipeline_bytes": (_sz, [_i64, _i64]),
     "pic_slice_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _f32, _f32,
                                          _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),

@@ -91,6 +91,60 @@ def decode_streams(strings: Sequence[bytes], indexes, tables: CdfTables, threads
     return torch.from_numpy(out.reshape(ix.shape))
 
 
+def _to_host_many(*tensors) -> List[np.ndarray]:
+    """[streams, ...] int32 tensors / arrays -> contiguous host [streams, n] arrays; CUDA tensors share one pinned copy."""
+    first = tensors[0]
+    if isinstance(first, torch.Tensor) and first.is_cuda:
+        both = torch.stack([t.to(torch.int32).reshape(first.shape[0], -1) for t in tensors])
+        host = torch.empty(both.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(both, non_blocking=False)
+        return [host[i].numpy() for i in range(len(tensors))]
+    arrs = [_i32(t) for t in tensors]
+    if any(a.shape != arrs[0].shape for a in arrs):
+        raise ValueError("symbols, indexes and level should have the same size.")
+    return [a.reshape(a.shape[0], -1) for a in arrs]
+
+
+def encode_levels(symbols, indexes, level, n_levels: int, tables: CdfTables, level_begin: int = 0,
+                  threads: int = 0) -> List[List[bytes]]:
+    """Progressive multi-level packing (functions_encode.py:176-196): bitstream[l][s] == the reference's
+    compress(symbols * delta_l, indexes * delta_l)[s] with delta_l = (level == l), for l in [level_begin, n_levels).
+    symbols / indexes / level cross PCIe once for all levels; (level, stream) pairs run on host threads."""
+    s, ix, lv = _to_host_many(symbols, indexes, level)
+    streams, n = s.shape
+    stride = int(lib().pic_rans_stream_bound(n))
+    tasks = (n_levels - level_begin) * streams
+    out = np.empty((tasks, stride), dtype=np.uint8)
+    nbytes = np.zeros(tasks, dtype=np.int64)
+    check(lib().pic_rans_encode_levels(_p(s), _p(ix), _p(lv), streams, n, level_begin, n_levels, *tables.args(), _p(out),
+                                       stride, _p(nbytes), threads), "pic_rans_encode_levels")
+    return [[out[l * streams + k, : nbytes[l * streams + k]].tobytes() for k in range(streams)]
+            for l in range(n_levels - level_begin)]
+
+
+def decode_levels(bitstream: Sequence[Sequence[bytes]], indexes, level, tables: CdfTables, level_begin: int = 0,
+                  out: Optional[torch.Tensor] = None, threads: int = 0) -> torch.Tensor:
+    """Inverse of encode_levels for the levels received so far: int32 symbols (CPU tensor shaped like `indexes`),
+    zero (or `out`'s previous content) where the element's level has not been received."""
+    ix, lv = _to_host_many(indexes, level)
+    streams, n = ix.shape
+    flat = [b for lvl in bitstream for b in lvl]
+    if any(len(lvl) != streams for lvl in bitstream):
+        raise ValueError("Invalid strings or indexes parameters")
+    sizes = np.array([len(b) for b in flat], dtype=np.int64)
+    padded = (sizes + 3) // 4 * 4
+    offs = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+    blob = np.zeros(int(padded.sum()) + 4, dtype=np.uint8)
+    for o, b in zip(offs, flat):
+        blob[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    shape = tuple(indexes.shape)
+    res = np.zeros((streams, n), dtype=np.int32) if out is None else _i32(out).reshape(streams, n).copy()
+    check(lib().pic_rans_decode_levels(_p(blob), _p(offs), _p(sizes), _p(ix), _p(lv), streams, n, level_begin,
+                                       level_begin + len(bitstream), *tables.args(), _p(res), threads),
+          "pic_rans_decode_levels")
+    return torch.from_numpy(res.reshape(shape))
+
+
 def _to_host_pair(symbols, indexes) -> Tuple[np.ndarray, np.ndarray]:
     if isinstance(symbols, torch.Tensor) and symbols.is_cuda:
         # one D2H copy of both tensors through pinned memory instead of per-element .tolist()

@@ -66,8 +66,10 @@ inline void enc_put_bits(uint64_t &x, Writer &w, uint32_t val) {
     x = (x << kBypassBits) | val;
 }
 
+// level != nullptr: progressive level `lv` -- elements of other levels are coded as (symbol 0, index 0), which is
+// what the reference's symbols * delta / indexes * delta tensors hold there (functions_encode.py:186-190).
 int64_t encode_stream(const int32_t *symbols, const int32_t *indexes, int64_t n, const Tables &t, uint8_t *out,
-                      int64_t out_cap) {
+                      int64_t out_cap, const int32_t *level = nullptr, int32_t lv = 0) {
     if (out_cap < 8 || (reinterpret_cast<uintptr_t>(out) & 3u)) return PIC_ERR_WORKSPACE;
     Writer w;
     w.begin = reinterpret_cast<uint32_t *>(out);
@@ -75,11 +77,12 @@ int64_t encode_stream(const int32_t *symbols, const int32_t *indexes, int64_t n,
     uint32_t *const end = w.ptr;
     uint64_t x = kRansL;
     for (int64_t i = n - 1; i >= 0; --i) {
-        const int32_t ci = indexes[i];
+        const bool on = !level || level[i] == lv;
+        const int32_t ci = on ? indexes[i] : 0;
         if (ci < 0 || ci >= t.n_cdfs) return PIC_ERR_INVALID_ARGUMENT;
         const int32_t *cdf = t.cdfs + static_cast<int64_t>(ci) * t.stride;
         const int32_t max_value = t.sizes[ci] - 2;
-        int64_t value = static_cast<int64_t>(symbols[i]) - t.offsets[ci];
+        int64_t value = static_cast<int64_t>(on ? symbols[i] : 0) - t.offsets[ci];
         uint64_t raw = 0;
         bool escaped = false;
         if (value < 0) {
@@ -129,7 +132,7 @@ inline uint32_t dec_get_bits(uint64_t &x, Reader &r) {
 }
 
 int decode_stream(const uint8_t *stream, int64_t nbytes, const int32_t *indexes, int64_t n, const Tables &t,
-                  int32_t *out) {
+                  int32_t *out, const int32_t *level = nullptr, int32_t lv = 0) {
     if (nbytes < 8 || (nbytes & 3) || (reinterpret_cast<uintptr_t>(stream) & 3u)) return PIC_ERR_INVALID_ARGUMENT;
     Reader r;
     r.ptr = reinterpret_cast<const uint32_t *>(stream);
@@ -138,7 +141,8 @@ int decode_stream(const uint8_t *stream, int64_t nbytes, const int32_t *indexes,
     r.ptr += 2;
     constexpr uint64_t mask = (1ull << kPrecision) - 1;
     for (int64_t i = 0; i < n; ++i) {
-        const int32_t ci = indexes[i];
+        const bool on = !level || level[i] == lv;
+        const int32_t ci = on ? indexes[i] : 0;
         if (ci < 0 || ci >= t.n_cdfs) return PIC_ERR_INVALID_ARGUMENT;
         const int32_t *cdf = t.cdfs + static_cast<int64_t>(ci) * t.stride;
         const int32_t size = t.sizes[ci];
@@ -168,7 +172,7 @@ int decode_stream(const uint8_t *stream, int64_t nbytes, const int32_t *indexes,
             else value += max_value;
         }
         if (r.underflow) return PIC_ERR_INVALID_ARGUMENT;
-        out[i] = static_cast<int32_t>(value + t.offsets[ci]);
+        if (on) out[i] = static_cast<int32_t>(value + t.offsets[ci]);
     }
     return PIC_OK;
 }
@@ -281,6 +285,42 @@ int pic_rans_decode_batch(const uint8_t *in, const int64_t *in_offsets, const in
         return PIC_ERR_INVALID_ARGUMENT;
     return run_streams(streams, threads, [&](int64_t s) {
         return decode_stream(in + in_offsets[s], in_bytes[s], indexes + s * n, n, t, symbols_out + s * n);
+    });
+}
+
+int pic_rans_encode_levels(const int32_t *symbols, const int32_t *indexes, const int32_t *level, int64_t streams,
+                           int64_t n, int level_begin, int level_end, const int32_t *cdfs, int n_cdfs, int cdf_stride,
+                           const int32_t *cdf_sizes, const int32_t *offsets, uint8_t *out, int64_t out_stride,
+                           int64_t *out_bytes, int threads) {
+    const Tables t{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
+    if (streams <= 0 || n < 0 || level_begin < 0 || level_end <= level_begin || !symbols || !indexes || !level || !out ||
+        !out_bytes || (out_stride & 3) || !tables_ok(t))
+        return PIC_ERR_INVALID_ARGUMENT;
+    const int64_t tasks = static_cast<int64_t>(level_end - level_begin) * streams;
+    return run_streams(tasks, threads, [&](int64_t k) {
+        const int64_t s = k % streams;
+        const int32_t lv = level_begin + static_cast<int32_t>(k / streams);
+        const int64_t b = encode_stream(symbols + s * n, indexes + s * n, n, t, out + k * out_stride, out_stride,
+                                        level + s * n, lv);
+        out_bytes[k] = b < 0 ? 0 : b;
+        return b < 0 ? static_cast<int>(b) : PIC_OK;
+    });
+}
+
+int pic_rans_decode_levels(const uint8_t *in, const int64_t *in_offsets, const int64_t *in_bytes,
+                           const int32_t *indexes, const int32_t *level, int64_t streams, int64_t n, int level_begin,
+                           int level_end, const int32_t *cdfs, int n_cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                           const int32_t *offsets, int32_t *symbols_out, int threads) {
+    const Tables t{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
+    if (streams <= 0 || n < 0 || level_begin < 0 || level_end <= level_begin || !in || !in_offsets || !in_bytes ||
+        !indexes || !level || !symbols_out || !tables_ok(t))
+        return PIC_ERR_INVALID_ARGUMENT;
+    // levels of one stream write disjoint elements of symbols_out[s], so (level, stream) tasks are independent
+    const int64_t tasks = static_cast<int64_t>(level_end - level_begin) * streams;
+    return run_streams(tasks, threads, [&](int64_t k) {
+        const int64_t s = k % streams;
+        const int32_t lv = level_begin + static_cast<int32_t>(k / streams);
+        return decode_stream(in + in_offsets[k], in_bytes[k], indexes + s * n, n, t, symbols_out + s * n, level + s * n, lv);
     });
 }
 

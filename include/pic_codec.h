@@ -61,6 +61,30 @@ int pic_rans_decode_batch(const uint8_t *in, const int64_t *in_offsets, const in
                           int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
                           int32_t *symbols_out, int threads);
 
+/*
+ * Progressive multi-level packing (test/functions_encode.py:176-196, functions_decode.py:186-206): the
+ * reference codes, per level l, the tensors symbols * delta_l and indexes * delta_l with
+ * delta_l = ProgMask(q_l) - ProgMask(q_{l-1}).  With the level map of pic_level_map (level[i] = l  <=>
+ * delta_l[i] = 1) the selection happens inside the coder: stream (l, s) codes, for i in [0, n),
+ * (level[s][i] == l ? symbols[s][i] : 0,  level[s][i] == l ? indexes[s][i] : 0) -- byte-identical to the
+ * reference's per-level streams -- so symbols, indexes and level cross PCIe ONCE for all levels.
+ * Streams are ordered [level][stream]; stream (l, s) is written at out + (l * streams + s) * out_stride and
+ * its length stored in out_bytes[l * streams + s].  Levels [level_begin, level_end) are coded.
+ */
+int pic_rans_encode_levels(const int32_t *symbols, const int32_t *indexes, const int32_t *level,
+                           int64_t streams, int64_t n, int level_begin, int level_end, const int32_t *cdfs,
+                           int n_cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                           uint8_t *out, int64_t out_stride, int64_t *out_bytes, int threads);
+/*
+ * Decoder side: streams of levels [level_begin, level_end) (same ordering; in_offsets / in_bytes indexed
+ * [(l - level_begin) * streams + s]) -> symbols_out[s][i] = decoded symbol where level[s][i] is one of those
+ * levels, untouched elsewhere (initialise it to zero, or to the symbols of the levels already received).
+ */
+int pic_rans_decode_levels(const uint8_t *in, const int64_t *in_offsets, const int64_t *in_bytes,
+                           const int32_t *indexes, const int32_t *level, int64_t streams, int64_t n,
+                           int level_begin, int level_end, const int32_t *cdfs, int n_cdfs, int cdf_stride,
+                           const int32_t *cdf_sizes, const int32_t *offsets, int32_t *symbols_out, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,6 @@ if torch.cuda.is_available():
     t_gpu, st2 = med(run)
     assert st2 == streams
     print(f"device tensors -> compress() ({levels} levels)  {t_gpu * 1e3:7.2f} ms  = {total / t_gpu / 1e6:8.1f} Msym/s")
+    t_lv, st3 = med(lambda: codec.encode_levels(ds, di, dl, levels, gcd._tables()))
+    assert st3 == streams
+    print(f"device tensors -> encode_levels() (one D2H, {levels} levels)  {t_lv * 1e3:7.2f} ms  = {total / t_lv / 1e6:8.1f} Msym/s")

@@ -141,3 +141,25 @@ def test_errors(tables):
         c.decode_with_indexes(s[:12], [5, 9, 0, 63] * 50, tables, None, None)  # truncated: runs out of words
     with pytest.raises(ValueError):
         codec.CdfTables(np.zeros(5, np.int32), [5], [0])
+
+
+def test_level_streams_equal_per_level_masked_streams(gold, tables):
+    """encode_levels(symbols, indexes, level) == compress(symbols * delta_l, indexes * delta_l) for every level
+    (functions_encode.py:176-196), and decode_levels restores exactly the received levels."""
+    rng = np.random.default_rng(9)
+    streams, n, levels = 5, 1777, 4
+    idx = rng.integers(0, 64, size=(streams, n)).astype(np.int32)
+    sym = np.rint(rng.normal(0, 1, (streams, n)) * gold["scale_table"][idx] * rng.choice([1, 1, 6], size=(streams, n)))
+    sym = sym.astype(np.int32)
+    level = rng.integers(0, levels + 1, size=(streams, n)).astype(np.int32)   # value `levels` = never sent
+    bits = codec.encode_levels(sym, idx, level, levels, tables, threads=3)
+    assert len(bits) == levels and all(len(b) == streams for b in bits)
+    for l in range(levels):
+        d = (level == l).astype(np.int32)
+        assert bits[l] == codec.encode_streams(sym * d, idx * d, tables), l
+    got = codec.decode_levels(bits[:2], idx, level, tables)
+    assert np.array_equal(got.numpy(), sym * (level < 2))
+    more = codec.decode_levels(bits[2:], idx, level, tables, level_begin=2, out=got)   # the next levels arrive
+    assert np.array_equal(more.numpy(), sym * (level < levels))
+    part = codec.encode_levels(sym, idx, level, levels, tables, level_begin=2)
+    assert part == bits[2:]

@@ -64,6 +64,11 @@ def test_progressive_encode_decode_round_trip():
                                      want=("y_hat", "mask"))
         assert torch.equal(part["mask"].reshape(kept.shape), kept)
         assert torch.equal(part["y_hat"].reshape(kept.shape), r_hat + T(mu).reshape(kept.shape))
+    # level-aware coder: symbols / indexes / level cross PCIe once; streams identical to the per-level compress()
+    packed = pic.codec.encode_levels(symbols, indexes, level, len(q_list), gc._tables())
+    assert packed == bitstream
+    got = pic.codec.decode_levels(packed[:2], dec_idx, level, gc._tables())
+    assert torch.equal(got.to(dev), symbols * (level < 2))
     assert torch.equal(r_hat, symbols.float())
     assert torch.equal(r_hat + T(mu).reshape(r_hat.shape), full["y_hat"].reshape(r_hat.shape))
     assert 0 < total_bytes < symbols.numel() * 4
