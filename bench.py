@@ -383,6 +383,7 @@ def run_cuda(args, wl):
     # host scheduling of N processes on one box does not leak into a device measurement; the same K steps issued
     # eagerly are timed first and reported as eager_ms_per_step.  NCCL steps (tiled, N > 1) stay eager.
     run_step, eager_ms = step, None
+    # (capturing the NCCL step was tried at N = 2: 2.5 % faster, but the process group then hangs at teardown)
     use_graph = bool(args.graph) and not (name == "tile8192" and world > 1)
     if use_graph:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -570,7 +571,7 @@ def main():
     ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
                     help="kodak_sweep: all (slice, q) units of a step in one launch, or one launch per slice index")
-    ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default)")
+    ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default; NCCL steps stay eager)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
