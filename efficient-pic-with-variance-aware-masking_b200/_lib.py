@@ -13,7 +13,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libpic_latent.so")
+LIB_PATH = os.environ.get("PIC_LIB_PATH") or os.path.join(_PKG, "libpic_latent.so")   # override: kernel experiments
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu", "pic_rans.cpp")]
 _HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh")] + [
     os.path.join(_ROOT, "include", "pic_latent.h"), os.path.join(_ROOT, "include", "pic_codec.h")]

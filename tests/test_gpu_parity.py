@@ -595,6 +595,18 @@ def test_large_unit_sampled_select_and_fallback(pic, dev):
         assert np.all((N(a) <= N(thr)) & (N(thr) <= N(b)) | np.isnan(rthr))
     s1, f1 = _select_counters(pic)
     assert s1 > s0 and f1 > f0, "both the sampled branch and the fallback must have run"
+    # a caller whose workspace is one byte short of pic_workspace_bytes gets the plain radix rounds: same thresholds
+    L = pic.lib()
+    t_std = T(std, dev)
+    ws_bytes = int(L.pic_workspace_bytes(n, len(rows)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    thr_small = torch.empty(len(rows), dtype=torch.float32, device=dev)
+    rc = L.pic_select_threshold(t_std.data_ptr(), n, len(rows), pic.ops.pr_to_q01(2.5), None, thr_small.data_ptr(), None,
+                                None, ws.data_ptr(), ws_bytes - 1, None)
+    assert rc == 0
+    assert np.array_equal(N(thr_small), po.channel_mask(std, 2.5)[1], equal_nan=True)
+    assert L.pic_select_threshold(t_std.data_ptr(), n, len(rows), pic.ops.pr_to_q01(2.5), None, thr_small.data_ptr(), None,
+                                  None, ws.data_ptr(), 64, None) == -3          # PIC_ERR_WORKSPACE
     # per-unit qualities incl. the ones / zeros sentinels, aligned n (vector sweep)
     n = 1 << 18
     std = np.stack([rng.gamma(2.0, 1.0, n).astype(np.float32) for _ in range(4)])
