@@ -71,6 +71,7 @@ constexpr int kScratchWords = 192;  // block_select uses [0,48); small-set helpe
 constexpr int kTableSmem = 64;
 constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
 constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
+constexpr int kWideThreads = 1024;         // latency variant of the select-only kernel (units <= SM count)
 constexpr int kRoundChunk = 16384;         // elements per CTA in hist_round_kernel
 constexpr int64_t kTwoKernelMinElems = int64_t(1) << 22;  // >= 4 Mi elements: select kernel + apply kernel
 constexpr int64_t kTwoKernelMinUnit = 32768;               // ... and units of at least this many elements
@@ -317,10 +318,12 @@ __device__ __forceinline__ double block_sum_f64(float v, double *sh /* THREADS/3
 //   4. the exact ranks are found among the candidates with the shared-memory radix select.
 // Returns false (uniformly) when the bracket missed or overflowed; the caller then runs the
 // full histogram select.  NaN presence is reported through scratch[39].
-template <int THREADS, bool VEC>
+// WIDE (latency variants of the select-only kernel, one or two wide CTAs per SM): a 4 x THREADS float4 park
+// area outside the histogram, so every thread keeps four 128-bit loads in flight whatever the CTA width.
+template <int THREADS, bool VEC, bool WIDE = false>
 __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32_t lo, uint32_t hi,
                                                uint32_t *hist, uint32_t *cand, uint32_t *scratch,
-                                               uint32_t &a_key, uint32_t &b_key) {
+                                               uint32_t &a_key, uint32_t &b_key, float4 *park_wide = nullptr) {
     const int tid = threadIdx.x;
     int S = n >> 4;                    // ~6 % of the unit's cache lines are touched by the sample
     S = S < 1024 ? 1024 : (S > kSampleMax ? kSampleMax : S);
@@ -370,12 +373,14 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
     uint32_t below = 0;
     bool has_nan = false;
     if (VEC) {
-        constexpr int VPI = (THREADS <= 256) ? 4 : 2;            // float4 per thread per iteration (16 KB park area)
+        // float4 per thread per iteration: the 16 KB histogram region parks 4 x 256 float4; wider CTAs get
+        // their own park area (kWideThreads) or fewer loads in flight (512)
+        constexpr int VPI = (THREADS <= 256 || WIDE) ? 4 : 2;
         const int nvec = n >> 2;
         const uint64_t pol_last = policy_evict_last();
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
-        float4 *park4 = reinterpret_cast<float4 *>(hist);
-        const float *park = reinterpret_cast<const float *>(hist) + tid * 4;
+        float4 *park4 = WIDE ? park_wide : reinterpret_cast<float4 *>(hist);
+        const float *park = reinterpret_cast<const float *>(park4) + tid * 4;
         f2 below2 = pk(0.0f, 0.0f);
         auto classify4 = [&](const float4 &q, uint32_t &hits4) {   // hits4: bits 0..3 of this float4
             const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
@@ -486,6 +491,10 @@ struct FusedSmem {
 // dynamic shared memory: max(select buffers, cp.async stage buffer) -- the two are never live
 // at the same time (select finishes before the unit's apply sweep starts)
 constexpr size_t kSelectSmemBytes = (2 * kHistBins + kCandMax) * sizeof(uint32_t);
+template <int THREADS, int OUTS>
+__host__ __device__ constexpr bool wide_select() { return OUTS == -3 /* kOutsSelectOnly */ && THREADS > 256; }
+template <int THREADS>
+__host__ __device__ constexpr size_t wide_park_bytes() { return size_t(4) * THREADS * sizeof(float4); }   // 32 KB (512) / 64 KB (1024)
 template <bool TRAIN, int THREADS>
 constexpr size_t fused_dyn_smem() {
     const size_t stage = size_t(2) * (TRAIN ? 5 : 4) * THREADS * sizeof(float4);
@@ -500,6 +509,8 @@ slice_fused_kernel(const SliceParams p) {
     float4 *stage = p.use_stage ? reinterpret_cast<float4 *>(dyn_smem) : nullptr;
     uint32_t *hist = reinterpret_cast<uint32_t *>(dyn_smem);
     uint32_t *cand = hist + 2 * kHistBins;
+    constexpr bool WIDE = wide_select<THREADS, OUTS>();
+    float4 *park_wide = WIDE ? reinterpret_cast<float4 *>(dyn_smem + kSelectSmemBytes) : nullptr;
     uint32_t *scratch = sm.scratch;
     const int n = static_cast<int>(p.n);
     const int tid = threadIdx.x;
@@ -534,7 +545,7 @@ slice_fused_kernel(const SliceParams p) {
                 if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
                 __syncthreads();
                 block_select_norm<THREADS>(cand, n, 0u, 32, hist, scratch, lo, hi, a_key, b_key);
-            } else if (sampled_select<THREADS, VEC>(std_u, n, lo, hi, hist, cand, scratch, a_key, b_key)) {
+            } else if (sampled_select<THREADS, VEC, WIDE>(std_u, n, lo, hi, hist, cand, scratch, a_key, b_key, park_wide)) {
                 if (tid == 0) atomicAdd(&g_sampled_units, 1ull);
             } else {
                 if (tid == 0) atomicAdd(&g_fallback_units, 1ull);
@@ -1115,7 +1126,9 @@ static int launch_fused_t(const SliceParams &p_in, cudaStream_t stream) {
     auto kern = slice_fused_kernel<TRAIN, VEC, THREADS, OUTS>;
     SliceParams p = p_in;
     p.use_stage = (VEC && p.apply_kind == 2) ? 1 : 0;
-    const size_t smem = (OUTS == kOutsSelectOnly) ? kSelectSmemBytes : fused_dyn_smem<TRAIN, THREADS>();
+    const size_t smem = (OUTS == kOutsSelectOnly)
+                            ? kSelectSmemBytes + (wide_select<THREADS, OUTS>() ? wide_park_bytes<THREADS>() : 0)
+                            : fused_dyn_smem<TRAIN, THREADS>();
     static bool configured = false;  // per instantiation
     static int occ_blocks[2] = {0, 0};
     if (!configured) {
@@ -1139,6 +1152,10 @@ static int launch_fused_v(const SliceParams &p, cudaStream_t stream) {
     // few large units: wider CTAs finish each unit sooner; otherwise 4 x 256-thread CTAs per SM
     // give the best overlap of one unit's (latency-bound) select with other units' apply sweeps
     static const int forced = [] { const char *e = getenv("PIC_FUSED_THREADS"); return e ? atoi(e) : 0; }();
+    // select-only with at most one unit per SM (per-slice launches, single images): one 1024-thread CTA per SM
+    // with 64 KB of loads in flight sweeps a unit ~3x sooner than 512 threads with 16 KB
+    if (OUTS == kOutsSelectOnly && (forced == kWideThreads || (forced == 0 && p.n > 16384 && p.units <= sm_count())))
+        return launch_fused_t<false, VEC, kWideThreads, kOutsSelectOnly>(p, stream);
     if (forced == 512 || (forced == 0 && p.n > 16384 && p.units < 2 * static_cast<int64_t>(sm_count())))
         return launch_fused_t<TRAIN, VEC, 512, OUTS>(p, stream);
     return launch_fused_t<TRAIN, VEC, 256, OUTS>(p, stream);

@@ -9,7 +9,7 @@ if not os.path.isfile(SO):
     csrc = os.path.join(ROOT, "efficient-pic-with-variance-aware-masking_b200", "csrc")
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                     "-DPIC_PHASE_TIMING", "-DPIC_PHASE_BLOCK=0", "-o", SO, os.path.join(csrc, "pic_latent.cu"),
-                    os.path.join(csrc, "pic_host.cu")], check=True)
+                    os.path.join(csrc, "pic_host.cu"), os.path.join(csrc, "pic_rans.cpp")], check=True)
 L = ctypes.CDLL(SO)
 vp, i64, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float
 L.pic_select_threshold.argtypes = [vp, i64, i64, f32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
