@@ -18,7 +18,7 @@ from . import _lib, codec, distributed, ops
 from ._lib import LIB_PATH, build, lib
 from .channel_mask import ChannelMask, ste_round
 from .entropy_models import EntropyModel, GaussianConditional, LowerBound
-from .functional import progressive_slice_forward, rate_bpp
+from .functional import lrp_merge, progressive_slice_forward, rate_bpp, rem_merge
 
 SCALES_MIN = 0.11
 SCALES_MAX = 256
@@ -31,4 +31,4 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
 
 
 __all__ = ["ChannelMask", "ste_round", "EntropyModel", "GaussianConditional", "LowerBound",
-           "progressive_slice_forward", "rate_bpp", "get_scale_table", "ops", "codec", "distributed", "build", "lib", "LIB_PATH"]
+           "progressive_slice_forward", "rate_bpp", "lrp_merge", "rem_merge", "get_scale_table", "ops", "codec", "distributed", "build", "lib", "LIB_PATH"]

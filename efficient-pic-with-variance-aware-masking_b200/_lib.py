@@ -54,6 +54,10 @@ SIGNATURES = {
     "pic_select_finish": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "pic_channel_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pic_attention_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "pic_lrp_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "pic_lrp_merge_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pic_rem_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "pic_rem_merge_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "pic_mask_from_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "pic_slice_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _f32,
                                     _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -1061,6 +1061,47 @@ __global__ void __launch_bounds__(256) mask_from_threshold_kernel(const float *s
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Elementwise neighbours of the path, one pass each instead of three:
+//   LRP epilogue + merge  (models/pic.py:635-641):  out = (y_hat + 0.5 * tanh(lrp)) + base
+//   REM merge             (layers/rem.py:137-140):  out = identity + ret * att_mask
+// KIND 0 forward LRP, 1 backward LRP (g_lrp = g * 0.5 * (1 - tanh(lrp)^2)), 2 forward REM, 3 backward REM (g * mask)
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float neighbour_op(float a, float b, float c, bool has_c) {
+    if (KIND == 0) {
+        const float t = __fadd_rn(a, __fmul_rn(0.5f, tanhf(b)));
+        return has_c ? __fadd_rn(t, c) : t;
+    }
+    if (KIND == 1) {
+        const float th = tanhf(b);
+        return __fmul_rn(a, __fmul_rn(0.5f, __fsub_rn(1.0f, __fmul_rn(th, th))));
+    }
+    if (KIND == 2) return __fadd_rn(a, __fmul_rn(b, c));
+    return __fmul_rn(a, b);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) neighbour_kernel(const float *a, const float *b, const float *c, float *out,
+                                                        int64_t n, bool vec) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool has_c = c != nullptr;
+    if (vec) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t j = t0; j < (n >> 2); j += stride) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(a) + j);
+            const float4 y = __ldg(reinterpret_cast<const float4 *>(b) + j);
+            const float4 w = has_c ? __ldg(reinterpret_cast<const float4 *>(c) + j) : z;
+            reinterpret_cast<float4 *>(out)[j] =
+                make_float4(neighbour_op<KIND>(x.x, y.x, w.x, has_c), neighbour_op<KIND>(x.y, y.y, w.y, has_c),
+                            neighbour_op<KIND>(x.z, y.z, w.z, has_c), neighbour_op<KIND>(x.w, y.w, w.w, has_c));
+        }
+        return;
+    }
+    for (int64_t j = t0; j < n; j += stride) out[j] = neighbour_op<KIND>(a[j], b[j], has_c ? c[j] : 0.0f, has_c);
+}
+
 // Progressive level map (test/functions_encode.py:176-190, functions_decode.py:186-200): for thresholds
 // thr[u][0..Q) of increasing quality, level[e] = first l with std[e] >= thr[u][l], or Q when no level keeps
 // the element.  The delta mask of level l (ProgMask(q_l) - ProgMask(q_{l-1})) is exactly (level == l).
@@ -1786,6 +1827,39 @@ int pic_dequantize(const int32_t *symbols, const float *means, int64_t n, float 
     dequantize_kernel<<<elementwise_grid(n, vec ? 4 : 1), 256, 0, static_cast<cudaStream_t>(stream_)>>>(symbols, means, n,
                                                                                                        out, vec);
     return launch_status();
+}
+
+static int launch_neighbour(int kind, const float *a, const float *b, const float *c, float *out, int64_t n,
+                            pic_stream_t stream_) {
+    if (n <= 0 || !a || !b || !out) return PIC_ERR_INVALID_ARGUMENT;
+    bool vec = (n % 4 == 0);
+    for (const void *q : {static_cast<const void *>(a), static_cast<const void *>(b), static_cast<const void *>(c),
+                          static_cast<const void *>(out)}) {
+        if (q && !aligned4(q)) return PIC_ERR_UNALIGNED;
+        if (q && !aligned16(q)) vec = false;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int grid = elementwise_grid(n, vec ? 4 : 1);
+    if (kind == 0) neighbour_kernel<0><<<grid, 256, 0, stream>>>(a, b, c, out, n, vec);
+    else if (kind == 1) neighbour_kernel<1><<<grid, 256, 0, stream>>>(a, b, c, out, n, vec);
+    else if (kind == 2) neighbour_kernel<2><<<grid, 256, 0, stream>>>(a, b, c, out, n, vec);
+    else neighbour_kernel<3><<<grid, 256, 0, stream>>>(a, b, c, out, n, vec);
+    return launch_status();
+}
+
+int pic_lrp_merge(const float *y_hat, const float *lrp, const float *base, float *out, int64_t n, pic_stream_t stream) {
+    return launch_neighbour(0, y_hat, lrp, base, out, n, stream);
+}
+int pic_lrp_merge_backward(const float *g_out, const float *lrp, float *g_lrp, int64_t n, pic_stream_t stream) {
+    return launch_neighbour(1, g_out, lrp, nullptr, g_lrp, n, stream);
+}
+int pic_rem_merge(const float *identity, const float *ret, const float *att_mask, float *out, int64_t n,
+                  pic_stream_t stream) {
+    if (!att_mask) return PIC_ERR_INVALID_ARGUMENT;
+    return launch_neighbour(2, identity, ret, att_mask, out, n, stream);
+}
+int pic_rem_merge_backward(const float *g_out, const float *att_mask, float *g_ret, int64_t n, pic_stream_t stream) {
+    return launch_neighbour(3, g_out, att_mask, nullptr, g_ret, n, stream);
 }
 
 int pic_log_sum(const float *x, int64_t n_per_unit, int64_t units, double *out, pic_stream_t stream_) {

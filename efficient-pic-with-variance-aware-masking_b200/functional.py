@@ -98,3 +98,70 @@ def rate_bpp(likelihoods: torch.Tensor, num_pixels: int) -> torch.Tensor:
 
     total = ops.log_sum(likelihoods.contiguous(), 1).sum()
     return total / (-math.log(2) * num_pixels)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# elementwise neighbours of the path: one fused pass each, with autograd
+# ---------------------------------------------------------------------------------------------------------------
+def _same(*ts):
+    shape = ts[0].shape
+    for t in ts:
+        if t is not None and t.shape != shape:
+            raise ValueError("tensors must have the same shape")
+    return [None if t is None else ops._require(t, "tensor") for t in ts]
+
+
+class _LrpMerge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_hat, lrp, base):
+        y_hat, lrp, base = _same(y_hat, lrp, base)
+        out = torch.empty_like(y_hat)
+        ops.check(ops.lib().pic_lrp_merge(ops._ptr(y_hat), ops._ptr(lrp), ops._ptr(base), ops._ptr(out), out.numel(),
+                                          ops._stream()), "pic_lrp_merge")
+        ctx.save_for_backward(lrp)
+        ctx.has_base = base is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (lrp,) = ctx.saved_tensors
+        g = g.contiguous()
+        g_lrp = None
+        if ctx.needs_input_grad[1]:
+            g_lrp = torch.empty_like(lrp)
+            ops.check(ops.lib().pic_lrp_merge_backward(ops._ptr(g), ops._ptr(lrp), ops._ptr(g_lrp), g.numel(),
+                                                       ops._stream()), "pic_lrp_merge_backward")
+        return (g if ctx.needs_input_grad[0] else None, g_lrp, g if (ctx.has_base and ctx.needs_input_grad[2]) else None)
+
+
+def lrp_merge(y_hat_slice: torch.Tensor, lrp: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """models/pic.py:635-641 in one pass:  `lrp = 0.5 * torch.tanh(lrp); y_hat_slice += lrp;
+    y_hat_slice = self.merge(y_hat_slice, y_hat_slices[current_index])`  (merge = sum; base=None skips it)."""
+    return _LrpMerge.apply(y_hat_slice, lrp, base)
+
+
+class _RemMerge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, identity, ret, att_mask):
+        identity, ret, att_mask = _same(identity, ret, att_mask)
+        out = torch.empty_like(identity)
+        ops.check(ops.lib().pic_rem_merge(ops._ptr(identity), ops._ptr(ret), ops._ptr(att_mask), ops._ptr(out),
+                                          out.numel(), ops._stream()), "pic_rem_merge")
+        ctx.save_for_backward(att_mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (att_mask,) = ctx.saved_tensors
+        g = g.contiguous()
+        g_ret = None
+        if ctx.needs_input_grad[1]:
+            g_ret = torch.empty_like(g)
+            ops.check(ops.lib().pic_rem_merge_backward(ops._ptr(g), ops._ptr(att_mask), ops._ptr(g_ret), g.numel(),
+                                                       ops._stream()), "pic_rem_merge_backward")
+        return (g if ctx.needs_input_grad[0] else None), g_ret, None
+
+
+def rem_merge(identity: torch.Tensor, ret: torch.Tensor, att_mask: torch.Tensor) -> torch.Tensor:
+    """layers/rem.py:137-140 in one pass:  `ret = ret * att_mask; res = identity + ret`."""
+    return _RemMerge.apply(identity, ret, att_mask)

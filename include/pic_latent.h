@@ -147,6 +147,22 @@ int pic_attention_mask(const float *std, int64_t n_per_unit, int64_t units, floa
                        const float *q01_per_unit, int copies, float *mask, float *thr_out, void *ws,
                        size_t ws_bytes, pic_stream_t stream);
 
+/*
+ * Elementwise neighbours of the path, one pass each instead of three torch kernels.
+ * LRP epilogue + merge (models/pic.py:635-641, rem_pic.py equivalents):
+ *     out = (y_hat + 0.5 * tanh(lrp)) + base          base nullable (no merge); out may alias y_hat
+ *     backward: g_y_hat = g_base = g_out;  g_lrp = g_out * 0.5 * (1 - tanh(lrp)^2)
+ * REM merge (layers/rem.py:137-140):
+ *     out = identity + ret * att_mask                 backward: g_identity = g_out; g_ret = g_out * att_mask
+ */
+int pic_lrp_merge(const float *y_hat, const float *lrp, const float *base, float *out, int64_t n,
+                  pic_stream_t stream);
+int pic_lrp_merge_backward(const float *g_out, const float *lrp, float *g_lrp, int64_t n, pic_stream_t stream);
+int pic_rem_merge(const float *identity, const float *ret, const float *att_mask, float *out, int64_t n,
+                  pic_stream_t stream);
+int pic_rem_merge_backward(const float *g_out, const float *att_mask, float *g_ret, int64_t n,
+                           pic_stream_t stream);
+
 /* mask = (std >= thr[u]) with thresholds already known (e.g. all-reduced ones). */
 int pic_mask_from_threshold(const float *std, const float *thr, int64_t n_per_unit,
                             int64_t units, float *mask, pic_stream_t stream);

@@ -198,3 +198,21 @@ def num_threads() -> int:
 
 def set_num_threads(n: int) -> None:
     lib().pic_oracle_set_num_threads(C.c_int(int(n)))
+
+
+# ---- elementwise neighbours of the path; numpy f32, same operation order as the reference ----
+def lrp_merge(y_hat, lrp, base=None):
+    """models/pic.py:635-641: lrp = 0.5 * tanh(lrp); y_hat += lrp; merge(y_hat, base) = y_hat + base."""
+    t = np.float32(0.5) * np.tanh(_c32(lrp))
+    out = _c32(y_hat) + t.astype(np.float32)
+    return out if base is None else (out + _c32(base)).astype(np.float32)
+
+
+def lrp_merge_backward(g_out, lrp):
+    th = np.tanh(_c32(lrp).astype(np.float64))
+    return (_c32(g_out).astype(np.float64) * 0.5 * (1.0 - th * th)).astype(np.float32)
+
+
+def rem_merge(identity, ret, att_mask):
+    """layers/rem.py:137-140: identity + ret * att_mask."""
+    return (_c32(identity) + (_c32(ret) * _c32(att_mask)).astype(np.float32)).astype(np.float32)

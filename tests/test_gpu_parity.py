@@ -617,3 +617,29 @@ def test_large_unit_sampled_select_and_fallback(pic, dev):
         assert np.array_equal(N(mask[u]), rmask[0]), pr
         if 0 < pr < 10:
             assert N(thr)[u] == rthr[0]
+
+
+@pytest.mark.parametrize("n", [4096 * 5, 1001])
+def test_elementwise_neighbours(pic, dev, n):
+    """LRP epilogue + merge (pic.py:635-641) and REM merge (rem.py:137-140), forward vs the
+    oracle, gradients vs torch autograd of the reference's own expressions."""
+    rng = np.random.default_rng(n)
+    y_hat, lrp, base, ret = (rng.normal(0, 2, n).astype(np.float32) for _ in range(4))
+    mask = (rng.random(n) < 0.4).astype(np.float32)
+    ty, tl, tb, tr = (T(a, dev).requires_grad_(True) for a in (y_hat, lrp, base, ret))
+    out = pic.lrp_merge(ty, tl, tb)
+    ref = po.lrp_merge(y_hat, lrp, base)
+    np.testing.assert_allclose(N(out), ref, rtol=1e-5, atol=1e-6)        # tanh: 1e-5 relative (north_star)
+    np.testing.assert_allclose(N(pic.lrp_merge(ty, tl)), po.lrp_merge(y_hat, lrp), rtol=1e-5, atol=1e-6)
+    g = torch.randn(n, device=dev)
+    out.backward(g)
+    y2, l2, b2 = (T(a, dev).requires_grad_(True) for a in (y_hat, lrp, base))
+    ((y2 + 0.5 * torch.tanh(l2)) + b2).backward(g)                        # the reference's expression
+    assert torch.equal(ty.grad, y2.grad) and torch.equal(tb.grad, b2.grad)
+    np.testing.assert_allclose(N(tl.grad), N(l2.grad), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(N(tl.grad), po.lrp_merge_backward(N(g), lrp), rtol=1e-4, atol=1e-6)
+    ident = T(base, dev).requires_grad_(True)
+    res = pic.rem_merge(ident, tr, T(mask, dev))
+    assert np.array_equal(N(res), po.rem_merge(base, ret, mask))
+    res.backward(g)
+    assert torch.equal(ident.grad, g) and torch.equal(tr.grad, g * T(mask, dev))
