@@ -286,6 +286,7 @@ def run_cuda(args, wl):
 
     fused = n <= int(L.pic_fused_max_elems())
     launches = [0]
+    tile_comm = None
     PLAN_KERNEL = {0: "slice_fused_kernel", 1: "slice_apply_kernel", 2: "slice_apply_kernel"}
     main_kernel = "slice_fused_kernel"
 
@@ -297,6 +298,14 @@ def run_cuda(args, wl):
         outs = {k: torch.empty((units, n_local), dtype=torch.int32 if k == "idx" else torch.float32, device=dev)
                 for k in want}
         backend = pdist.CudaTileBackend(std, units) if world > 1 else None
+        if world > 1 and not args.torch_collectives:
+            # collectives issued inside libpic_latent.so (one host call per select); checked once against the
+            # torch.distributed protocol: thresholds must be bit-identical
+            tile_comm = pdist.NcclTileComm(dev)
+            t_c = pdist.tiled_select_threshold(std, units, n, q_all, comm=tile_comm)
+            t_t = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
+            if not torch.equal(t_c, t_t):
+                raise RuntimeError("tiled select: library-issued NCCL path disagrees with the torch.distributed path")
         main_kernel = "slice_apply_kernel" if (world == 1 or n_local > int(L.pic_fused_max_elems())) else "slice_fused_kernel"
 
         def step():
@@ -304,9 +313,9 @@ def run_cuda(args, wl):
                 ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
                 launches[0] = plan(n, units)[1]   # pivot + sweep + cluster select + apply = 4
             else:
-                thr = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
+                thr = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend, comm=tile_comm)
                 ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr, want=want, out=outs)
-                launches[0] = 9          # same local kernels; + 4 NCCL all-reduces (not counted)
+                launches[0] = 9          # begin + 3 x (hist, advance) + finish + apply; + 4 NCCL all-reduces (not counted)
         elems_per_rank = units * n_local
         total_elems = units * n
     elif name == "first_train":
@@ -538,6 +547,8 @@ def run_cuda(args, wl):
                 "algorithmic_bytes_per_elem": kbytes, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": kern_ms, "other_kernels": other,
                 "whole_step_frac": (elems_per_rank * wl["bytes_per_elem"] / (ms_per_step * 1e-3) / 1e9) / hbm}
+    if tile_comm is not None:
+        tile_comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -553,7 +564,9 @@ def run_cuda(args, wl):
                    "cuda_graph": use_graph,
                    "launches_per_step": launches[0], "outputs": list(want), "bytes_per_elem": wl["bytes_per_elem"],
                    "l2": f"inputs of one step = {elems_per_rank * 16 / 1e6:.0f} MB per GPU > 126 MB L2, no explicit flush",
-                   "parallelism": (f"{world} rank(s), row-band tiles + NCCL histogram all-reduce" if name == "tile8192"
+                   "parallelism": (f"{world} rank(s), row-band tiles + NCCL histogram all-reduce"
+                                   + (" issued by libpic_latent.so" if tile_comm is not None else " over torch.distributed")
+                                   if name == "tile8192"
                                    else f"{world} rank(s), units sharded, no collective")},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
     }
@@ -572,6 +585,8 @@ def main():
     ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
                     help="kodak_sweep: all (slice, q) units of a step in one launch, or one launch per slice index")
     ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default; NCCL steps stay eager)")
+    ap.add_argument("--torch-collectives", action="store_true",
+                    help="tile8192, N > 1: carry the histogram all-reduces over torch.distributed instead of the library's own NCCL calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -29,7 +29,7 @@ Q_ONES = -1.0
 Q_ZEROS = 2.0
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 _tables = [_vp, _i32, _i32, _vp, _vp]   # cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets (include/pic_codec.h)
@@ -52,6 +52,11 @@ SIGNATURES = {
     "pic_hist_round": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
     "pic_select_advance": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "pic_select_finish": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "pic_tiled_workspace_bytes": (_sz, [_i64]),
+    "pic_dist_unique_id": (C.c_int, [_vp]),
+    "pic_dist_comm_init": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "pic_dist_comm_destroy": (C.c_int, [_vp]),
+    "pic_tiled_select_threshold": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "pic_channel_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pic_attention_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "pic_lrp_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),

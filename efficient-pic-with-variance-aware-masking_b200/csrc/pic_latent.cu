@@ -17,9 +17,12 @@
 //   gaussian_* / build_indexes / quantize / dequantize / log_sum   un-fused operators
 // All global accesses are 128-bit when n % 4 == 0 and the pointers are 16-byte aligned.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time (dlopen), never linked
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/pic_latent.h"
 #include "pic_math.cuh"
@@ -1617,6 +1620,103 @@ int pic_select_finish(const void *state, const uint32_t *min_above, int64_t unit
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(
         static_cast<const SelectState *>(state), min_above, units, thr_out, a_out, b_out);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatially tiled select with NCCL issued from this library (one call = begin + 3 x (histogram kernel,
+// all-reduce, advance) + min all-reduce + finish on the caller's stream: no host work between the steps).
+// NCCL is the copy torch already loaded (dlopen of libnccl.so.2); uint32 sum / min are native NCCL types.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    decltype(&ncclGetUniqueId) get_unique_id = nullptr;
+    decltype(&ncclCommInitRank) comm_init_rank = nullptr;
+    decltype(&ncclCommDestroy) comm_destroy = nullptr;
+    decltype(&ncclAllReduce) all_reduce = nullptr;
+    bool ok = false;
+};
+const NcclApi &nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the one already in the process (torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!h) {
+            const char *path = getenv("PIC_NCCL_LIB");
+            if (path) h = dlopen(path, RTLD_NOW);
+        }
+        if (!h) return a;
+        a.get_unique_id = reinterpret_cast<decltype(a.get_unique_id)>(dlsym(h, "ncclGetUniqueId"));
+        a.comm_init_rank = reinterpret_cast<decltype(a.comm_init_rank)>(dlsym(h, "ncclCommInitRank"));
+        a.comm_destroy = reinterpret_cast<decltype(a.comm_destroy)>(dlsym(h, "ncclCommDestroy"));
+        a.all_reduce = reinterpret_cast<decltype(a.all_reduce)>(dlsym(h, "ncclAllReduce"));
+        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce;
+        return a;
+    }();
+    return api;
+}
+inline int nccl_status(ncclResult_t r) {
+    if (r == ncclSuccess) return PIC_OK;
+    pic::g_last_cuda_error = 100000 + static_cast<int>(r);   // NCCL results are reported above the CUDA range
+    return PIC_ERR_CUDA;
+}
+}  // namespace
+
+size_t pic_tiled_workspace_bytes(int64_t units) { return rounds_ws_bytes(units < 1 ? 1 : units); }
+
+int pic_dist_unique_id(unsigned char *id_out) {
+    static_assert(sizeof(ncclUniqueId) == PIC_DIST_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!id_out) return PIC_ERR_INVALID_ARGUMENT;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    ncclUniqueId id;
+    const int rc = nccl_status(nccl_api().get_unique_id(&id));
+    if (rc == PIC_OK) memcpy(id_out, &id, sizeof(id));
+    return rc;
+}
+
+int pic_dist_comm_init(const unsigned char *id, int rank, int world_size, void **comm_out) {
+    if (!id || !comm_out || world_size < 1 || rank < 0 || rank >= world_size) return PIC_ERR_INVALID_ARGUMENT;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    const int rc = nccl_status(nccl_api().comm_init_rank(&comm, world_size, uid, rank));
+    *comm_out = comm;
+    return rc;
+}
+
+int pic_dist_comm_destroy(void *comm) {
+    if (!comm) return PIC_OK;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    return nccl_status(nccl_api().comm_destroy(static_cast<ncclComm_t>(comm)));
+}
+
+int pic_tiled_select_threshold(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                               const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm_,
+                               pic_stream_t stream_) {
+    int rc = check_common(n_total, units);
+    if (rc != PIC_OK) return rc;
+    if (n_local < 0 || n_local > n_total || (n_local > 0 && !std_local) || !thr_out || !comm_) return PIC_ERR_INVALID_ARGUMENT;
+    if (!ws || ws_bytes < rounds_ws_bytes(units)) return PIC_ERR_WORKSPACE;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    RoundsWs w = carve_ws(ws, units);
+    select_begin_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, n_total, units, q01,
+                                                                                      q01_per_unit);
+    rc = launch_status();
+    for (int r = 0; r < 3 && rc == PIC_OK; ++r) {
+        rc = launch_hist_round(std_local, n_local, units, r, w.state, w.hist[r], w.min_above, stream);
+        if (rc == PIC_OK)
+            rc = nccl_status(nccl_api().all_reduce(w.hist[r], w.hist[r], static_cast<size_t>(units) * kHistWords, ncclUint32,
+                                                   ncclSum, comm, stream));
+        if (rc == PIC_OK) rc = launch_advance(w.state, w.hist[r], units, r, stream);
+    }
+    if (rc != PIC_OK) return rc;
+    rc = nccl_status(nccl_api().all_reduce(w.min_above, w.min_above, static_cast<size_t>(units), ncclUint32, ncclMin, comm, stream));
+    if (rc != PIC_OK) return rc;
+    select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
+                                                                                      thr_out, nullptr, nullptr);
     return launch_status();
 }
 

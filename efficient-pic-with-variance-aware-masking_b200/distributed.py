@@ -72,6 +72,49 @@ class CudaTileBackend:
         return thr
 
 
+class NcclTileComm:
+    """NCCL communicator owned by libpic_latent.so for `pic_tiled_select_threshold` (C ABI 1c): the whole tiled
+    select becomes ONE host call that enqueues kernels and collectives on the current stream.  The 128-byte
+    unique id travels over torch.distributed (`group`), which must already be initialised."""
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            check(lib().pic_dist_unique_id(buf), "pic_dist_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(device) if dist.get_backend(group) == "nccl" else ident
+        dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(ident.cpu().tolist())
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            check(lib().pic_dist_comm_init(raw, rank, world, ctypes.byref(handle)), "pic_dist_comm_init")
+        self.handle, self.device, self.world = handle, device, world
+        self._ws = None
+
+    def select_threshold(self, std_local: torch.Tensor, units: int, n_total: int, q01) -> torch.Tensor:
+        std_local = ops._require(std_local, "std_local")
+        n_local = std_local.numel() // units
+        q, qt = ops._q_args(q01, units, std_local.device)
+        thr = torch.empty(units, dtype=torch.float32, device=std_local.device)
+        need = int(lib().pic_tiled_workspace_bytes(units))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=std_local.device)
+        check(lib().pic_tiled_select_threshold(ops._ptr(std_local), n_local, n_total, units, q, ops._ptr(qt), ops._ptr(thr),
+                                               ops._ptr(self._ws), self._ws.numel(), self.handle, ops._stream()),
+              "pic_tiled_select_threshold")
+        return thr
+
+    def close(self) -> None:
+        if self.handle:
+            torch.cuda.synchronize(self.device)
+            check(lib().pic_dist_comm_destroy(self.handle), "pic_dist_comm_destroy")
+            self.handle = None
+
+
 def allreduce_min_u32(keys_i32: torch.Tensor, group=None) -> torch.Tensor:
     """MIN over ranks of uint32 keys stored in an int32 tensor (torch has no uint32 collectives):
     flipping the top bit maps unsigned order onto signed order."""
@@ -81,9 +124,12 @@ def allreduce_min_u32(keys_i32: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def tiled_select_threshold(std_local: Optional[torch.Tensor], units: int, n_total: int, q01, group=None,
-                           backend=None) -> torch.Tensor:
+                           backend=None, comm: Optional[NcclTileComm] = None) -> torch.Tensor:
     """Global per-unit quantile threshold of units whose elements are spread over the ranks of
-    `group`.  Returns thr [units], bit-identical on every rank."""
+    `group`.  Returns thr [units], bit-identical on every rank.  `comm` (NcclTileComm): the collectives are
+    issued inside the library (one host call); otherwise torch.distributed carries them round by round."""
+    if comm is not None:
+        return comm.select_threshold(std_local, units, n_total, q01)
     be = backend if backend is not None else CudaTileBackend(std_local, units)
     be.begin(n_total, q01)
     for rnd in range(3):
@@ -96,7 +142,7 @@ def tiled_select_threshold(std_local: Optional[torch.Tensor], units: int, n_tota
 
 def tiled_slice_forward(y_top, y_base, mu, std, units: int, n_total: int, pr, scale_table=None, noise=None,
                         group=None, scale_bound: float = 0.11, lik_bound: float = 1e-9,
-                        want=("mask", "y_hat", "lik")) -> dict:
+                        want=("mask", "y_hat", "lik"), comm: Optional[NcclTileComm] = None) -> dict:
     """One progressive slice of spatially tiled units: all-reduced threshold + local apply."""
     q01 = pr if isinstance(pr, torch.Tensor) else ops.pr_to_q01(pr)
     mode_scalar = None if isinstance(q01, torch.Tensor) else q01
@@ -104,7 +150,7 @@ def tiled_slice_forward(y_top, y_base, mu, std, units: int, n_total: int, pr, sc
         # ones / zeros short-circuit: no threshold, no collective
         return ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise,
                                  scale_bound=scale_bound, lik_bound=lik_bound, want=want)
-    thr = tiled_select_threshold(std, units, n_total, q01, group)
+    thr = tiled_select_threshold(std, units, n_total, q01, group, comm=comm)
     res = ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise, thr_in=thr,
                             scale_bound=scale_bound, lik_bound=lik_bound, want=want)
     res["thr"] = thr

@@ -130,6 +130,23 @@ int pic_select_finish(const void *state, const uint32_t *min_above, int64_t unit
                       float *a_out, float *b_out, pic_stream_t stream);
 
 /*
+ * (1c) The same protocol with the collectives issued by this library: one call enqueues begin, 3 x (histogram
+ * kernel, ncclAllReduce(uint32, sum), advance), ncclAllReduce(uint32, min) and finish on `stream` -- no host work
+ * between the steps (the Python loop over pic_hist_round + torch.distributed costs ~10 us of host time per
+ * step, more than the kernels at 8 GPUs).  NCCL is bound at run time to the libnccl.so.2 already loaded in the
+ * process (torch's); the communicator is created from a 128-byte unique id that the caller broadcasts over its
+ * own channel (torch.distributed, MPI, a file).  ws: pic_tiled_workspace_bytes(units) bytes (~25 KB per unit).
+ */
+#define PIC_DIST_ID_BYTES 128
+size_t pic_tiled_workspace_bytes(int64_t units);
+int pic_dist_unique_id(unsigned char *id_out);                                /* rank 0 */
+int pic_dist_comm_init(const unsigned char *id, int rank, int world_size, void **comm_out);
+int pic_dist_comm_destroy(void *comm);
+int pic_tiled_select_threshold(const float *std_local, int64_t n_local, int64_t n_total, int64_t units,
+                               float q01, const float *q01_per_unit, float *thr_out, void *ws,
+                               size_t ws_bytes, void *comm, pic_stream_t stream);
+
+/*
  * (2) ChannelMask.forward / ProgMask (channel_mask.py:18-49, 89-151): mask = (std >= thr) as
  * f32 {0,1}; ones / zeros for the sentinels.  thr_out nullable.
  */

@@ -643,3 +643,33 @@ def test_elementwise_neighbours(pic, dev, n):
     assert np.array_equal(N(res), po.rem_merge(base, ret, mask))
     res.backward(g)
     assert torch.equal(ident.grad, g) and torch.equal(tr.grad, g * T(mask, dev))
+
+
+def test_library_issued_nccl_select_world_size_1(pic, dev):
+    """pic_tiled_select_threshold (C ABI 1c) on a one-rank NCCL communicator created by the library: same
+    thresholds as the single-device select (the N > 1 agreement with the torch.distributed protocol is asserted by
+    bench.py --workload tile8192 at start-up)."""
+    import ctypes
+
+    L = pic.lib()
+    ident = (ctypes.c_ubyte * 128)()
+    assert L.pic_dist_unique_id(ident) == 0
+    comm = ctypes.c_void_p()
+    assert L.pic_dist_comm_init(ident, 0, 1, ctypes.byref(comm)) == 0 and comm.value
+    rng = np.random.default_rng(3)
+    units, n = 3, 70001
+    std = trained_like(rng, (units, n))[3]
+    std[1, :100] = 0.25
+    ts = T(std, dev)
+    thr = torch.empty(units, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(L.pic_tiled_workspace_bytes(units)), dtype=torch.uint8, device=dev)
+    q = pic.ops.q01_tensor([2.5, 7.0, 10.0], dev)
+    rc = L.pic_tiled_select_threshold(ts.data_ptr(), n, n, units, 0.0, q.data_ptr(), thr.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), comm, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = pic.ops.select_threshold(ts, units, q)
+    assert torch.equal(thr[:2], want[:2]) and float(thr[2]) == float("-inf")
+    _, rthr = po.channel_mask(std[:2], [2.5, 7.0])
+    assert np.array_equal(N(thr[:2]), rthr)
+    assert L.pic_dist_comm_destroy(comm) == 0
