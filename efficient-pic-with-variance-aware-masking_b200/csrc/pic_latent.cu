@@ -1634,6 +1634,8 @@ struct NcclApi {
     decltype(&ncclCommInitRank) comm_init_rank = nullptr;
     decltype(&ncclCommDestroy) comm_destroy = nullptr;
     decltype(&ncclAllReduce) all_reduce = nullptr;
+    decltype(&ncclGroupStart) group_start = nullptr;
+    decltype(&ncclGroupEnd) group_end = nullptr;
     bool ok = false;
 };
 const NcclApi &nccl_api() {
@@ -1650,7 +1652,9 @@ const NcclApi &nccl_api() {
         a.comm_init_rank = reinterpret_cast<decltype(a.comm_init_rank)>(dlsym(h, "ncclCommInitRank"));
         a.comm_destroy = reinterpret_cast<decltype(a.comm_destroy)>(dlsym(h, "ncclCommDestroy"));
         a.all_reduce = reinterpret_cast<decltype(a.all_reduce)>(dlsym(h, "ncclAllReduce"));
-        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce;
+        a.group_start = reinterpret_cast<decltype(a.group_start)>(dlsym(h, "ncclGroupStart"));
+        a.group_end = reinterpret_cast<decltype(a.group_end)>(dlsym(h, "ncclGroupEnd"));
+        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.group_start && a.group_end;
         return a;
     }();
     return api;
@@ -1705,15 +1709,24 @@ int pic_tiled_select_threshold(const float *std_local, int64_t n_local, int64_t 
     select_begin_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, n_total, units, q01,
                                                                                       q01_per_unit);
     rc = launch_status();
+    const NcclApi &nc = nccl_api();
     for (int r = 0; r < 3 && rc == PIC_OK; ++r) {
         rc = launch_hist_round(std_local, n_local, units, r, w.state, w.hist[r], w.min_above, stream);
+        if (rc != PIC_OK) break;
+        // the last round's kernel also produced the per-rank minimum key above the bucket: its MIN all-reduce
+        // rides in the same NCCL group (one fused launch) as the histogram's SUM all-reduce
+        if (r == 2) rc = nccl_status(nc.group_start());
         if (rc == PIC_OK)
-            rc = nccl_status(nccl_api().all_reduce(w.hist[r], w.hist[r], static_cast<size_t>(units) * kHistWords, ncclUint32,
-                                                   ncclSum, comm, stream));
+            rc = nccl_status(nc.all_reduce(w.hist[r], w.hist[r], static_cast<size_t>(units) * kHistWords, ncclUint32,
+                                           ncclSum, comm, stream));
+        if (r == 2) {
+            if (rc == PIC_OK)
+                rc = nccl_status(nc.all_reduce(w.min_above, w.min_above, static_cast<size_t>(units), ncclUint32, ncclMin, comm, stream));
+            const int rc_end = nccl_status(nc.group_end());
+            if (rc == PIC_OK) rc = rc_end;
+        }
         if (rc == PIC_OK) rc = launch_advance(w.state, w.hist[r], units, r, stream);
     }
-    if (rc != PIC_OK) return rc;
-    rc = nccl_status(nccl_api().all_reduce(w.min_above, w.min_above, static_cast<size_t>(units), ncclUint32, ncclMin, comm, stream));
     if (rc != PIC_OK) return rc;
     select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
                                                                                       thr_out, nullptr, nullptr);
