@@ -323,7 +323,12 @@ __device__ __forceinline__ double block_sum_f64(float v, double *sh /* THREADS/3
 // full histogram select.  NaN presence is reported through scratch[39].
 // WIDE (latency variants of the select-only kernel, one or two wide CTAs per SM): a 4 x THREADS float4 park
 // area outside the histogram, so every thread keeps four 128-bit loads in flight whatever the CTA width.
-template <int THREADS, bool VEC, bool WIDE = false>
+#ifdef PIC_SELECT_PIPE
+constexpr bool kSelectPipe = true;    // experiment: cp.async double-buffered park area in the 256-thread select
+#else
+constexpr bool kSelectPipe = false;
+#endif
+template <int THREADS, bool VEC, bool WIDE = false, bool PIPE = false>
 __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32_t lo, uint32_t hi,
                                                uint32_t *hist, uint32_t *cand, uint32_t *scratch,
                                                uint32_t &a_key, uint32_t &b_key, float4 *park_wide = nullptr) {
@@ -383,7 +388,7 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         const uint64_t pol_last = policy_evict_last();
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
         float4 *park4 = WIDE ? park_wide : reinterpret_cast<float4 *>(hist);
-        const float *park = reinterpret_cast<const float *>(park4) + tid * 4;
+        const float *park = reinterpret_cast<const float *>(park4) + tid * 4;   // the current iteration's slots
         f2 below2 = pk(0.0f, 0.0f);
         auto classify4 = [&](const float4 &q, uint32_t &hits4) {   // hits4: bits 0..3 of this float4
             const float mx = max_nan(max_nan(q.x, q.y), max_nan(q.z, q.w));
@@ -426,6 +431,37 @@ __device__ __forceinline__ bool sampled_select(const float *std_u, int n, uint32
         // warp-uniform trip counts (jb is the warp's first index): out-of-range lanes idle
         const int lane = tid & 31;
         int jb = tid - lane;
+        if (PIPE) {
+            // full iterations through two park buffers filled by cp.async: the next iteration's loads are in
+            // flight while this one is classified (per-thread private slots: no barrier needed)
+            float4 *const buf0 = reinterpret_cast<float4 *>(hist);
+            const int iters = nvec / (VPI * THREADS);
+            auto issue = [&](int it, int b) {
+#pragma unroll
+                for (int i = 0; i < VPI; ++i)
+                    cp_async16(static_cast<uint32_t>(__cvta_generic_to_shared((b ? park_wide : buf0) + i * THREADS + tid)),
+                               s4 + it * (VPI * THREADS) + i * THREADS + tid, pol_last);
+                cp_async_commit();
+            };
+            if (iters > 0) issue(0, 0);
+            for (int it = 0; it < iters; ++it) {
+                const int b = it & 1;
+                if (it + 1 < iters) {
+                    issue(it + 1, b ^ 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                const float4 *cur = b ? park_wide : buf0;
+                park = reinterpret_cast<const float *>(cur) + tid * 4;
+                uint32_t hits = 0;
+#pragma unroll
+                for (int i = 0; i < VPI; ++i) classify(cur[i * THREADS + tid], hits, 4 * i);
+                append(hits);
+            }
+            park = reinterpret_cast<const float *>(park4) + tid * 4;
+            jb += iters * VPI * THREADS;
+        }
         for (; jb + (VPI - 1) * THREADS + 31 < nvec; jb += VPI * THREADS) {   // VPI independent 128-bit loads in flight
             const int j = jb + lane;
             float4 v[VPI];
@@ -505,7 +541,7 @@ constexpr size_t fused_dyn_smem() {
 }
 
 template <bool TRAIN, bool VEC, int THREADS, int OUTS>
-__global__ void __launch_bounds__(THREADS, (OUTS == kOutsSelectOnly ? 1280 : 1024) / THREADS)
+__global__ void __launch_bounds__(THREADS, (OUTS == kOutsSelectOnly && !kSelectPipe ? 1280 : 1024) / THREADS)
 slice_fused_kernel(const SliceParams p) {
     __shared__ __align__(16) FusedSmem<THREADS> sm;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -513,7 +549,8 @@ slice_fused_kernel(const SliceParams p) {
     uint32_t *hist = reinterpret_cast<uint32_t *>(dyn_smem);
     uint32_t *cand = hist + 2 * kHistBins;
     constexpr bool WIDE = wide_select<THREADS, OUTS>();
-    float4 *park_wide = WIDE ? reinterpret_cast<float4 *>(dyn_smem + kSelectSmemBytes) : nullptr;
+    constexpr bool PIPE = kSelectPipe && OUTS == kOutsSelectOnly && THREADS == 256 && VEC;
+    float4 *park_wide = (WIDE || PIPE) ? reinterpret_cast<float4 *>(dyn_smem + kSelectSmemBytes) : nullptr;
     uint32_t *scratch = sm.scratch;
     const int n = static_cast<int>(p.n);
     const int tid = threadIdx.x;
@@ -548,7 +585,7 @@ slice_fused_kernel(const SliceParams p) {
                 if (__any_sync(0xffffffffu, has_nan) && (tid & 31) == 0) scratch[39] = 1u;
                 __syncthreads();
                 block_select_norm<THREADS>(cand, n, 0u, 32, hist, scratch, lo, hi, a_key, b_key);
-            } else if (sampled_select<THREADS, VEC, WIDE>(std_u, n, lo, hi, hist, cand, scratch, a_key, b_key, park_wide)) {
+            } else if (sampled_select<THREADS, VEC, WIDE, PIPE>(std_u, n, lo, hi, hist, cand, scratch, a_key, b_key, park_wide)) {
                 if (tid == 0) atomicAdd(&g_sampled_units, 1ull);
             } else {
                 if (tid == 0) atomicAdd(&g_fallback_units, 1ull);
@@ -1171,7 +1208,8 @@ static int launch_fused_t(const SliceParams &p_in, cudaStream_t stream) {
     SliceParams p = p_in;
     p.use_stage = (VEC && p.apply_kind == 2) ? 1 : 0;
     const size_t smem = (OUTS == kOutsSelectOnly)
-                            ? kSelectSmemBytes + (wide_select<THREADS, OUTS>() ? wide_park_bytes<THREADS>() : 0)
+                            ? kSelectSmemBytes + (wide_select<THREADS, OUTS>() ? wide_park_bytes<THREADS>()
+                                                  : (kSelectPipe && THREADS == 256 ? size_t(16384) : 0))
                             : fused_dyn_smem<TRAIN, THREADS>();
     static bool configured = false;  // per instantiation
     static int occ_blocks[2] = {0, 0};
