@@ -673,3 +673,38 @@ def test_library_issued_nccl_select_world_size_1(pic, dev):
     _, rthr = po.channel_mask(std[:2], [2.5, 7.0])
     assert np.array_equal(N(thr[:2]), rthr)
     assert L.pic_dist_comm_destroy(comm) == 0
+
+
+def test_randomised_slice_configurations(pic, dev):
+    """40 seeded random configurations (units, ragged n across all three launch plans, per-unit qualities incl. the
+    ones / zeros sentinels, optional y_base / noise / table, output subsets, input distributions) vs the oracle."""
+    rng = np.random.default_rng(20240607)
+    table_np = scale_table()
+    table = T(table_np, dev)
+    sizes = [1, 3, 31, 257, 4097, 5121, 8192, 20001, 32768, 49152, 131072, 131073, 150001, 262144]
+    for case in range(40):
+        units = int(rng.integers(1, 5))
+        n = int(sizes[rng.integers(len(sizes))]) if rng.random() < 0.8 else int(rng.integers(1, 60000))
+        y_top, y_base, mu, std = trained_like(rng, (units, n))
+        kind = rng.integers(4)
+        if kind == 1:
+            std = (np.round(std * 4) / 4).astype(np.float32)                    # heavy ties
+        elif kind == 2:
+            std = np.sort(std, axis=1)[:, ::-1].copy()                          # adversarial order
+        elif kind == 3:
+            std = (std * 0 + rng.choice([0.05, 0.11, 3.0])).astype(np.float32)  # constant
+        prs = [float(rng.choice([0.0, 10.0, 11.0, rng.uniform(0.01, 9.99)], p=[0.1, 0.1, 0.05, 0.75])) for _ in range(units)]
+        use_base, train, use_table = rng.random() < 0.7, rng.random() < 0.4, rng.random() < 0.7
+        nz = rng.uniform(-0.5, 0.5, size=(units, n)).astype(np.float32) if train else None
+        ref = po.slice_forward(y_top, y_base if use_base else None, mu, std, prs, table_np, noise=nz)
+        want = ["mask", "y_hat", "lik", "thr"] + (["idx"] if use_table else []) + (["symbols"] if rng.random() < 0.5 else [])
+        out = pic.ops.slice_forward(T(y_top, dev), T(y_base, dev) if use_base else None, T(mu, dev), T(std, dev), units,
+                                    pic.ops.q01_tensor(prs, dev), table if use_table else None,
+                                    noise=None if nz is None else T(nz, dev), want=tuple(want))
+        tag = (case, units, n, int(kind), prs, use_base, train)
+        keep = np.array([0 < p < 10 for p in prs])
+        assert np.array_equal(N(out["thr"])[keep], ref["thr"][keep], equal_nan=True), tag
+        for k in ("mask", "y_hat", "idx", "symbols"):
+            if k in want:
+                assert np.array_equal(N(out[k]), ref[k]), (k,) + tag
+        assert_lik_close(N(out["lik"]), ref["lik"])
