@@ -163,3 +163,13 @@ def test_level_streams_equal_per_level_masked_streams(gold, tables):
     assert np.array_equal(more.numpy(), sym * (level < levels))
     part = codec.encode_levels(sym, idx, level, levels, tables, level_begin=2)
     assert part == bits[2:]
+
+
+def test_empty_streams(gold, tables):
+    """n = 0: the stream is the bare rANS state (8 bytes), as the oracle writes it."""
+    lists = (gold["cdf"].tolist(), gold["cdf_length"].tolist(), gold["offset"].tolist())
+    empty = np.zeros(0, np.int32)
+    s = codec.RansCoder().encode_with_indexes(empty, empty, tables, None, None)
+    assert s == ro.encode_with_indexes([], [], *lists) and len(s) == 8
+    assert codec.RansCoder().decode_with_indexes(s, empty, tables, None, None) == []
+    assert codec.encode_streams(np.zeros((2, 0), np.int32), np.zeros((2, 0), np.int32), tables) == [s, s]
