@@ -59,47 +59,40 @@ class LowerBound(nn.Module):
         return _LowerBoundFn.apply(x, self.bound)
 
 
-class _EntropyCoder:
-    """Proxy to compressai's rANS coder (entropy_models.py:18-52); only built when compressai exists."""
+class _CompressaiCoder:
+    """The reference's coder handle (entropy_models.py:18-52) when compressai is importable: one object exposing
+    `encode_with_indexes` / `decode_with_indexes` of the named backend."""
+
+    _BACKENDS = {
+        "ans": lambda: __import__("compressai.ans", fromlist=["RansEncoder"]),
+        "rangecoder": lambda: __import__("range_coder"),
+    }
 
     def __init__(self, method):
-        if not isinstance(method, str):
+        if type(method) is not str:
             raise ValueError(f'Invalid method type "{type(method)}"')
-        from compressai import available_entropy_coders  # noqa: WPS433 (optional dependency)
+        import compressai
 
-        if method not in available_entropy_coders():
-            methods = ", ".join(available_entropy_coders())
-            raise ValueError(f'Unknown entropy coder "{method}" (available: {methods})')
-        if method == "ans":
-            from compressai import ans
-
-            encoder, decoder = ans.RansEncoder(), ans.RansDecoder()
-        elif method == "rangecoder":
-            import range_coder
-
-            encoder, decoder = range_coder.RangeEncoder(), range_coder.RangeDecoder()
+        known = compressai.available_entropy_coders()
+        if method not in known:
+            raise ValueError(f'Unknown entropy coder "{method}" (available: {", ".join(known)})')
+        mod = self._BACKENDS[method]()
+        enc, dec = (mod.RansEncoder(), mod.RansDecoder()) if method == "ans" else (mod.RangeEncoder(), mod.RangeDecoder())
         self.name = method
-        self._encoder = encoder
-        self._decoder = decoder
-
-    def encode_with_indexes(self, *args, **kwargs):
-        return self._encoder.encode_with_indexes(*args, **kwargs)
-
-    def decode_with_indexes(self, *args, **kwargs):
-        return self._decoder.decode_with_indexes(*args, **kwargs)
+        self.encode_with_indexes = enc.encode_with_indexes
+        self.decode_with_indexes = dec.decode_with_indexes
 
 
 def _make_entropy_coder(method):
+    """compressai's coder when it is installed (default method = compressai.get_entropy_coder()), else the
+    package's native rANS coder (codec.RansCoder), which speaks the same bit-stream."""
     try:
-        if method is None:
-            from compressai import get_entropy_coder
-
-            method = get_entropy_coder()
-        return _EntropyCoder(method)
+        import compressai
     except ImportError:
         if method not in (None, "ans"):
             raise ValueError(f'Unknown entropy coder "{method}" (available: ans)')
-        return codec.RansCoder()  # compressai absent: the native rANS coder of this package
+        return codec.RansCoder()
+    return _CompressaiCoder(compressai.get_entropy_coder() if method is None else method)
 
 
 class EntropyModel(nn.Module):
@@ -162,77 +155,72 @@ class EntropyModel(nn.Module):
         return cls.dequantize(inputs, means)
 
     # ---- rANS coding (206-294) ----------------------------------------------------------
-    def _check_cdf_size(self):
-        if self._quantized_cdf.numel() == 0:
-            raise ValueError("Uninitialized CDFs. Run update() first")
-        if len(self._quantized_cdf.size()) != 2:
-            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+    _TABLE_CHECKS = (   # (buffer, wanted rank, message when empty, message when the rank is wrong) -- reference 185-204
+        ("_quantized_cdf", 2, "Uninitialized CDFs. Run update() first", "Invalid CDF size {}"),
+        ("_cdf_length", 1, "Uninitialized CDF lengths. Run update() first", "Invalid offsets size {}"),
+        ("_offset", 1, "Uninitialized offsets. Run update() first", "Invalid offsets size {}"),
+    )
 
-    def _check_offsets_size(self):
-        if self._offset.numel() == 0:
-            raise ValueError("Uninitialized offsets. Run update() first")
-        if len(self._offset.size()) != 1:
-            raise ValueError(f"Invalid offsets size {self._offset.size()}")
-
-    def _check_cdf_length(self):
-        if self._cdf_length.numel() == 0:
-            raise ValueError("Uninitialized CDF lengths. Run update() first")
-        if len(self._cdf_length.size()) != 1:
-            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+    def _check_tables(self) -> None:
+        for name, rank, empty_msg, rank_msg in self._TABLE_CHECKS:
+            buf = getattr(self, name)
+            if buf.numel() == 0:
+                raise ValueError(empty_msg)
+            if buf.dim() != rank:
+                raise ValueError(rank_msg.format(buf.size()))
 
     def _tables(self) -> "codec.CdfTables":
         """Host copy of the CDF tables for the native coder, rebuilt when update() replaces the buffers."""
         key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, self._quantized_cdf.numel())
         if getattr(self, "_tables_key", None) != key:
-            self._check_cdf_size(), self._check_cdf_length(), self._check_offsets_size()
+            self._check_tables()
             self._tables_cache = codec.CdfTables(self._quantized_cdf, self._cdf_length, self._offset)
             self._tables_key = key
         return self._tables_cache
 
+    def _stream_lists(self):
+        """The tables as the Python lists compressai's coder takes."""
+        return (self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
+                self._offset.reshape(-1).int().tolist())
+
     def compress(self, inputs, indexes, means=None, flag=1, already_quantize=False):
-        symbols = self.quantize(inputs, "symbols", means) if already_quantize is False else inputs
-        if len(inputs.size()) < 2:
+        """entropy_models.py:206-241: one stream per entry of dim 0."""
+        symbols = inputs if already_quantize else self.quantize(inputs, "symbols", means)
+        if inputs.dim() < 2:
             raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
-        if symbols.size() != indexes.size():
+        if symbols.shape != indexes.shape:
             raise ValueError("`inputs` and `indexes` should have the same size.")
         if isinstance(self.entropy_coder, codec.RansCoder):
-            # one D2H copy of the int32 symbols / indexes, every stream (dim 0) on its own host thread
+            # one D2H copy of the int32 symbols / indexes, every stream on its own host thread
             return codec.encode_streams(symbols, indexes, self._tables())
-        strings = []
-        for i in range(symbols.size(0)):
-            rv = self.entropy_coder.encode_with_indexes(
-                symbols[i].reshape(-1).int().tolist(), indexes[i].reshape(-1).int().tolist(),
-                self._quantized_cdf.tolist(), self._cdf_length.reshape(-1).int().tolist(),
-                self._offset.reshape(-1).int().tolist())
-            strings.append(rv)
-        return strings
+        tables = self._stream_lists()
+        flat_s, flat_i = symbols.reshape(symbols.size(0), -1).int(), indexes.reshape(indexes.size(0), -1).int()
+        return [self.entropy_coder.encode_with_indexes(row_s.tolist(), row_i.tolist(), *tables)
+                for row_s, row_i in zip(flat_s, flat_i)]
 
     def decompress(self, strings, indexes, means=None, flag=1):
-        if not isinstance(strings, (tuple, list)):
+        """entropy_models.py:243-294."""
+        if type(strings) not in (tuple, list):
             raise ValueError("Invalid `strings` parameter type.")
-        if not len(strings) == indexes.size(0):
+        if len(strings) != indexes.size(0):
             raise ValueError("Invalid strings or indexes parameters")
-        if len(indexes.size()) < 2:
+        if indexes.dim() < 2:
             raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
-        self._check_cdf_size(), self._check_cdf_length(), self._check_offsets_size()
+        self._check_tables()
         if means is not None:
-            if means.size()[:2] != indexes.size()[:2]:
+            if tuple(means.shape[:2]) != tuple(indexes.shape[:2]):
                 raise ValueError("Invalid means or indexes parameters")
-            if means.size() != indexes.size():
-                for i in range(2, len(indexes.size())):
-                    if means.size(i) != 1:
-                        raise ValueError("Invalid means parameters")
-        cdf = self._quantized_cdf
+            if means.shape != indexes.shape and any(d != 1 for d in means.shape[2:]):
+                raise ValueError("Invalid means parameters")   # broadcastable means only
         if isinstance(self.entropy_coder, codec.RansCoder):
-            outputs = codec.decode_streams(strings, indexes, self._tables()).to(indexes.device)
-            return self.dequantize(outputs, means)
-        outputs = cdf.new_empty(indexes.size())
-        for i, s in enumerate(strings):
-            values = self.entropy_coder.decode_with_indexes(
-                s, indexes[i].reshape(-1).int().tolist(), cdf.tolist(),
-                self._cdf_length.reshape(-1).int().tolist(), self._offset.reshape(-1).int().tolist())
-            outputs[i] = torch.tensor(values, device=outputs.device, dtype=outputs.dtype).reshape(outputs[i].size())
-        return self.dequantize(outputs, means)
+            symbols = codec.decode_streams(strings, indexes, self._tables()).to(indexes.device)
+            return self.dequantize(symbols, means)
+        tables = self._stream_lists()
+        symbols = self._quantized_cdf.new_empty(indexes.size())
+        for k, stream in enumerate(strings):
+            vals = self.entropy_coder.decode_with_indexes(stream, indexes[k].reshape(-1).int().tolist(), *tables)
+            symbols[k] = torch.tensor(vals, device=symbols.device, dtype=symbols.dtype).reshape(symbols[k].shape)
+        return self.dequantize(symbols, means)
 
 
 class _QuantizeNoise(torch.autograd.Function):
@@ -273,73 +261,74 @@ class _GaussianForward(torch.autograd.Function):
 
 
 class GaussianConditional(EntropyModel):
+    """Constructor contract of the reference (entropy_models.py:531-567): `scale_table` is None or a non-empty,
+    sorted, positive list / tuple; `scale_bound` > 0 (defaults to 0.11; None takes the table's first entry)."""
+
     def __init__(self, scale_table: Optional[Union[List, Tuple]], *args: Any, scale_bound: float = 0.11,
                  tail_mass: float = 1e-9, **kwargs: Any):
         super().__init__(*args, **kwargs)
-        if not isinstance(scale_table, (type(None), list, tuple)):
-            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
-        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
-            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
-        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
-            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        if scale_table is not None:
+            if type(scale_table) not in (list, tuple):
+                raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+            if len(scale_table) == 0:
+                raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+            ascending = all(a <= b for a, b in zip(scale_table, scale_table[1:]))
+            if not ascending or min(scale_table) <= 0:
+                raise ValueError(f'Invalid scale_table "({scale_table})"')
         self.tail_mass = float(tail_mass)
         if scale_bound is None and scale_table:
-            scale_bound = self.scale_table[0]
-        if scale_bound <= 0:
+            scale_bound = float(scale_table[0])
+        if scale_bound is None or scale_bound <= 0:
             raise ValueError("Invalid parameters")
         self.lower_bound_scale = LowerBound(scale_bound)
         self.register_buffer("scale_table", self._prepare_scale_table(scale_table) if scale_table else torch.Tensor())
-        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]) if scale_bound is not None else None)
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
 
     @staticmethod
     def _prepare_scale_table(scale_table):
-        return torch.Tensor(tuple(float(s) for s in scale_table))
+        return torch.Tensor([float(s) for s in scale_table])
 
     def _standardized_cumulative(self, inputs: Tensor) -> Tensor:
-        half = float(0.5)
-        const = float(-(2 ** -0.5))
-        return half * torch.erfc(const * inputs)
+        """Phi(x) = erfc(-x / sqrt(2)) / 2 with the reference's constants (f32 erfc of c * x, c = float(-(2 ** -0.5)))."""
+        return float(0.5) * torch.erfc(float(-(2 ** -0.5)) * inputs)
 
     @staticmethod
     def _standardized_quantile(quantile):
-        import scipy.stats
+        from scipy.stats import norm
 
-        return scipy.stats.norm.ppf(quantile)
+        return norm.ppf(quantile)
 
     def update_scale_table(self, scale_table):
-        device = self.scale_table.device
-        self.scale_table = self._prepare_scale_table(scale_table).to(device)
-        self.update(self.scale_table)
+        self.update(scale_table)
         return True
 
     def update(self, scale_table):
-        """entropy_models.py:591-618: the pmf with the reference's own torch ops (f32, on the host: 64 rows), the
-        16-bit CDF rows through compressai's pmf_to_quantized_cdf when importable, else pic_pmf_to_quantized_cdf."""
+        """entropy_models.py:591-618.  Row i of the table describes round(N(0, s_i)) on the support
+        [-c_i, c_i], c_i = ceil(s_i * |Phi^-1(tail_mass / 2)|), plus one escape slot holding the two tails: its pmf is
+        computed with the reference's own torch ops in f32 (on the host: 64 rows) and normalised to 16-bit CDF rows by
+        compressai's pmf_to_quantized_cdf when importable, else pic_pmf_to_quantized_cdf (include/pic_codec.h)."""
         device = self.scale_table.device
         self.scale_table = self._prepare_scale_table(scale_table).to(device)
         try:
-            from compressai._CXX import pmf_to_quantized_cdf as _pmf_to_quantized_cdf
+            from compressai._CXX import pmf_to_quantized_cdf as normalise
         except ImportError:
-            _pmf_to_quantized_cdf = codec.pmf_to_quantized_cdf
-        table = self.scale_table.cpu()
-        multiplier = -self._standardized_quantile(self.tail_mass / 2)
-        pmf_center = torch.ceil(table * multiplier).int()
-        pmf_length = 2 * pmf_center + 1
-        max_length = torch.max(pmf_length).item()
-        samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
-        samples_scale = table.unsqueeze(1).float()
-        upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
-        lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
-        pmf = upper - lower
-        tail_mass = 2 * lower[:, :1]
-        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32)
-        for i, p in enumerate(pmf):
-            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
-            _cdf = torch.IntTensor(_pmf_to_quantized_cdf(prob.tolist(), self.entropy_coder_precision))
-            cdf[i, : _cdf.size(0)] = _cdf
-        self._quantized_cdf = cdf.to(device)
-        self._offset = (-pmf_center).to(device)
-        self._cdf_length = (pmf_length + 2).to(device)
+            normalise = codec.pmf_to_quantized_cdf
+        sigma = self.scale_table.cpu().float()
+        half_width = torch.ceil(sigma * -self._standardized_quantile(self.tail_mass / 2)).int()      # c_i
+        support = 2 * half_width + 1
+        widest = int(support.max())
+        # |k - c_i| for k = 0 .. widest-1 (int32, then f32), standardised by sigma_i: same operations as the reference
+        dist = (torch.arange(widest).int() - half_width[:, None]).abs().float()
+        upper = self._standardized_cumulative((0.5 - dist) / sigma[:, None])
+        lower = self._standardized_cumulative((-0.5 - dist) / sigma[:, None])
+        pmf, tails = upper - lower, 2 * lower[:, :1]
+        table = torch.zeros((sigma.numel(), widest + 2), dtype=torch.int32)
+        for row, (p, width, tail) in enumerate(zip(pmf, support.tolist(), tails)):
+            cdf_row = normalise(torch.cat((p[:width], tail)).tolist(), self.entropy_coder_precision)
+            table[row, : len(cdf_row)] = torch.tensor(cdf_row, dtype=torch.int32)
+        self._quantized_cdf = table.to(device)
+        self._offset = (-half_width).to(device)
+        self._cdf_length = (support + 2).to(device)
 
     # ---- hot path ---------------------------------------------------------------------------
     def _bounds(self) -> Tuple[float, float]:
