@@ -66,8 +66,41 @@ inline void enc_put_bits(uint64_t &x, Writer &w, uint32_t val) {
     x = (x << kBypassBits) | val;
 }
 
+// One (start, freq) pair prepared for division-free coding (Alverson reciprocal, as in ryg_rans'
+// Rans64EncSymbolInit): x' = x + bias + mulhi(x, rcp) >> shift * (2^16 - freq)  ==  ((x / freq) << 16) + x % freq + start.
+struct FastSym {
+    uint64_t rcp, x_max;
+    uint32_t shift, bias, cmpl;
+};
+FastSym fast_sym(uint32_t start, uint32_t freq) {
+    FastSym f;
+    f.x_max = ((kRansL >> kPrecision) << 32) * freq;
+    f.cmpl = (1u << kPrecision) - freq;
+    if (freq < 2) {   // 1 / 1 is not representable: mulhi(x, ~0) = x - 1, compensated in the bias
+        f.rcp = ~0ull;
+        f.shift = 0;
+        f.bias = start + (1u << kPrecision) - 1;
+    } else {
+        uint32_t sh = 0;
+        while (freq > (1u << sh)) ++sh;
+        f.rcp = static_cast<uint64_t>(((static_cast<unsigned __int128>(1) << (sh + 63)) + freq - 1) / freq);
+        f.shift = sh - 1;
+        f.bias = start;
+    }
+    return f;
+}
+inline void enc_put_fast(uint64_t &x, Writer &w, const FastSym &f) {
+    if (x >= f.x_max) {
+        w.put(static_cast<uint32_t>(x));
+        x >>= 32;
+    }
+    const uint64_t q = static_cast<uint64_t>((static_cast<unsigned __int128>(x) * f.rcp) >> 64) >> f.shift;
+    x = x + f.bias + q * f.cmpl;
+}
+
 // level != nullptr: progressive level `lv` -- elements of other levels are coded as (symbol 0, index 0), which is
-// what the reference's symbols * delta / indexes * delta tensors hold there (functions_encode.py:186-190).
+// what the reference's symbols * delta / indexes * delta tensors hold there (functions_encode.py:186-190).  That one
+// pair is 7/8 of all coding steps at 8 levels, so it takes the division-free form.
 int64_t encode_stream(const int32_t *symbols, const int32_t *indexes, int64_t n, const Tables &t, uint8_t *out,
                       int64_t out_cap, const int32_t *level = nullptr, int32_t lv = 0) {
     if (out_cap < 8 || (reinterpret_cast<uintptr_t>(out) & 3u)) return PIC_ERR_WORKSPACE;
@@ -76,8 +109,21 @@ int64_t encode_stream(const int32_t *symbols, const int32_t *indexes, int64_t n,
     w.ptr = w.begin + out_cap / 4;
     uint32_t *const end = w.ptr;
     uint64_t x = kRansL;
+    FastSym zero{};
+    bool zero_ok = false;   // (symbol 0, index 0) inside table 0's regular range?
+    if (level) {
+        const int64_t v0 = -static_cast<int64_t>(t.offsets[0]);
+        if (v0 >= 0 && v0 < t.sizes[0] - 2 && t.cdfs[v0 + 1] > t.cdfs[v0]) {
+            zero = fast_sym(static_cast<uint32_t>(t.cdfs[v0]), static_cast<uint32_t>(t.cdfs[v0 + 1] - t.cdfs[v0]));
+            zero_ok = true;
+        }
+    }
     for (int64_t i = n - 1; i >= 0; --i) {
         const bool on = !level || level[i] == lv;
+        if (!on && zero_ok) {
+            enc_put_fast(x, w, zero);
+            continue;
+        }
         const int32_t ci = on ? indexes[i] : 0;
         if (ci < 0 || ci >= t.n_cdfs) return PIC_ERR_INVALID_ARGUMENT;
         const int32_t *cdf = t.cdfs + static_cast<int64_t>(ci) * t.stride;
@@ -140,8 +186,27 @@ int decode_stream(const uint8_t *stream, int64_t nbytes, const int32_t *indexes,
     uint64_t x = static_cast<uint64_t>(r.ptr[0]) | (static_cast<uint64_t>(r.ptr[1]) << 32);
     r.ptr += 2;
     constexpr uint64_t mask = (1ull << kPrecision) - 1;
+    // elements of other levels were coded as (symbol 0, index 0): when the state's low bits fall in that slot (they
+    // do, for a valid stream) the table search is skipped
+    uint32_t z_start = 0, z_freq = 0;
+    if (level) {
+        const int64_t v0 = -static_cast<int64_t>(t.offsets[0]);
+        if (v0 >= 0 && v0 < t.sizes[0] - 2 && t.cdfs[v0 + 1] > t.cdfs[v0]) {
+            z_start = static_cast<uint32_t>(t.cdfs[v0]);
+            z_freq = static_cast<uint32_t>(t.cdfs[v0 + 1] - t.cdfs[v0]);
+        }
+    }
     for (int64_t i = 0; i < n; ++i) {
         const bool on = !level || level[i] == lv;
+        if (!on && z_freq != 0) {
+            const uint32_t rel = static_cast<uint32_t>(x & mask) - z_start;
+            if (rel < z_freq) {
+                x = z_freq * (x >> kPrecision) + rel;
+                if (x < kRansL) x = (x << 32) | r.get();
+                if (r.underflow) return PIC_ERR_INVALID_ARGUMENT;
+                continue;
+            }
+        }
         const int32_t ci = on ? indexes[i] : 0;
         if (ci < 0 || ci >= t.n_cdfs) return PIC_ERR_INVALID_ARGUMENT;
         const int32_t *cdf = t.cdfs + static_cast<int64_t>(ci) * t.stride;

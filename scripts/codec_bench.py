@@ -41,6 +41,13 @@ total = levels * slices * n
 nbytes = sum(len(b) for st in streams for b in st)
 print(f"native  encode {total / t_enc / 1e6:8.1f} Msym/s   decode {total / t_dec / 1e6:8.1f} Msym/s   "
       f"({levels} levels x {slices} streams x {n}; {nbytes} bytes = {8 * nbytes / (slices * n):.3f} bit/elem)")
+lvl32 = level.astype(np.int32)
+t_el, st_l = med(lambda: codec.encode_levels(sym, idx, lvl32, levels, tables))
+assert st_l == streams
+t_dl, back_l = med(lambda: codec.decode_levels(st_l, idx, lvl32, tables))
+assert np.array_equal(back_l.numpy(), sym)
+print(f"levels  encode {total / t_el / 1e6:8.1f} Msym/s   decode {total / t_dl / 1e6:8.1f} Msym/s   "
+      f"(encode_levels / decode_levels on host arrays: selection inside the coder, {t_el * 1e3:.2f} / {t_dl * 1e3:.2f} ms)")
 t1, _ = med(lambda: [codec.encode_streams(s, i, tables, threads=1) for s, i in per_level], reps=3)
 print(f"native  encode, 1 thread {total / t1 / 1e6:8.1f} Msym/s")
 c = codec.RansCoder()
