@@ -475,7 +475,8 @@ def run_cuda(args, wl):
             dt = float(tdt.item())
         e2e = {"value": total_elems * e2e_steps / dt / 1e9, "unit": "Gelem/s",
                "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 16),
-               "steps": e2e_steps, "per": "rank",
+               "steps": e2e_steps, "value_scope": "whole job (all ranks' elements / slowest rank's wall time)",
+               "bytes_scope": "per rank and step",
                "api": "pic_slice_forward_host (C ABI, pinned host buffers, 3-slot copy/compute pipeline)"}
         if rank == 0:
             assert torch.equal(host_out["mask"][:per_slice], outs["mask"][:per_slice].cpu()), "host/device mismatch"
