@@ -443,6 +443,8 @@ def run_cuda(args, wl):
     e2e = None
     if not args.no_e2e and name == "kodak_sweep":
         chunk = args.e2e_chunk if args.e2e_chunk > 0 else max(1, min(per_slice, (48 << 20) // (n * 4)))
+        all_cpus = os.sched_getaffinity(0)
+        numa_node = None if args.no_numa_bind else ops.bind_host_to_device_numa(dev)   # pinned buffers local to the GPU
         host_in = [t.cpu().pin_memory() for t in (y_top, y_base, mu, std)]
         q_host = q_all.cpu().pin_memory()
         host_out = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32).pin_memory()
@@ -477,9 +479,11 @@ def run_cuda(args, wl):
                "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 16),
                "steps": e2e_steps, "value_scope": "whole job (all ranks' elements / slowest rank's wall time)",
                "bytes_scope": "per rank and step",
+               "host_numa_node": numa_node,
                "api": "pic_slice_forward_host (C ABI, pinned host buffers, 3-slot copy/compute pipeline)"}
         if rank == 0:
             assert torch.equal(host_out["mask"][:per_slice], outs["mask"][:per_slice].cpu()), "host/device mismatch"
+        os.sched_setaffinity(0, all_cpus)   # the CPU baseline below gets every host core again
 
     # ---------------- roofline of the dominant kernel: CUDA events around that kernel alone ----------------
     hbm, which = peaks()
@@ -588,6 +592,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default; NCCL steps stay eager)")
     ap.add_argument("--torch-collectives", action="store_true",
                     help="tile8192, N > 1: carry the histogram all-reduces over torch.distributed instead of the library's own NCCL calls")
+    ap.add_argument("--no-numa-bind", action="store_true", help="e2e: do not bind the process to the GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

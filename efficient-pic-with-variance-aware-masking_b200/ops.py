@@ -60,6 +60,33 @@ def q01_tensor(prs: Sequence[Number], device) -> torch.Tensor:
     return torch.tensor(vals, dtype=torch.float32).to(device, non_blocking=True)
 
 
+def bind_host_to_device_numa(device) -> Optional[int]:
+    """Host-buffer callers (pic_slice_forward_host): restrict this process to the CPUs of the NUMA node the GPU
+    hangs off, so that pinned buffers allocated afterwards (first touch) are local to its PCIe root port.  Returns
+    the node, or None when the topology is not visible (containers) -- in which case nothing is changed."""
+    import os
+
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(device).pci_device_id
+        sysfs = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0"
+        node = int(open(os.path.join(sysfs, "numa_node")).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def _units_view(t: torch.Tensor, units: int) -> Tuple[int, int]:
     total = t.numel()
     if units <= 0 or total % units != 0:
