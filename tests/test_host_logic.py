@@ -132,3 +132,27 @@ def test_ops_reject_bad_inputs_without_touching_the_gpu():
         ops.quantize(torch.zeros(8), "nope")
     with pytest.raises(TypeError):
         ops._require(np.zeros(3), "x")
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The package (Python and CUDA/C++ sources) must not import, load or name the oracle, and nothing that runs on
+    the GPU box may read /root/reference: the oracle is test infrastructure, the reference does not travel."""
+    pkg = os.path.join(ROOT, "efficient-pic-with-variance-aware-masking_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                continue
+            text = open(os.path.join(base, f), errors="replace").read()
+            # comments may NAME the oracle (provenance of constants, what a test compares with); code may not
+            # import it, load its library or put its directory on a path
+            for pattern in (r"^\s*(import|from)\s+(oracle|pic_oracle|rans_oracle|ref_shim)\b", r"libpic_oracle", r"oracle/_build",
+                            r"oracle/_ref", r"sys\.path[^\n]*oracle", r"dlopen\([^\n]*oracle", r"/root/reference"):
+                if re.search(pattern, text, flags=re.M):
+                    offenders.append((f, pattern))
+    assert not offenders, offenders
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(ROOT, f)).read(), f
+    for f in os.listdir(os.path.join(ROOT, "tests")):
+        if f.endswith(".py") and f != os.path.basename(__file__):   # this file names the path in the check above
+            assert "/root/reference" not in open(os.path.join(ROOT, "tests", f)).read(), f
