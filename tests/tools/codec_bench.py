@@ -2,12 +2,12 @@
 level.  Reports the native coder (host threads, int32 buffers in place), the same through the reference's list
 boundary (`.tolist()` per stream, entropy_models.py:229-236), and the pure-Python oracle on a small sample.
 With a GPU: also symbols / indexes produced by the latent path on the device (one pinned D2H copy).
-usage: python scripts/codec_bench.py [levels]"""
+usage: python tests/tools/codec_bench.py [levels]"""
 import os, sys, time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pic_b200 as pic

@@ -1,6 +1,6 @@
 """Fallback rate / speed of the sampled select on spatially correlated std maps (real latents are smooth)."""
 import os, sys, ctypes
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, torch, torch.nn.functional as F
 import pic_b200
