@@ -387,8 +387,11 @@ gs_cluster_select_kernel(const GsParams p, int tiles_per_unit) {
     const int64_t v0 = nvec * crank / kClusterCtas, v1 = nvec * (crank + 1) / kClusterCtas;
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
     uint32_t prefix = 0, rank = lo, below_total = 0, count = 0, mn = 0xffffffffu, last_bin = 0;
+    uint32_t a_key = 0, b_key = 0;
+    bool resolved = false;   // uniform over the cluster (every CTA holds the same merged histograms)
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
+        if (resolved) break;
         constexpr int kUp[3] = {32, 21, 10};   // bits above round r's digit
         const int shift = round_shift(r), nbins = round_bins(r), up = kUp[r];
         uint32_t *h = hist[r & 1];
@@ -448,9 +451,27 @@ gs_cluster_select_kernel(const GsParams p, int tiles_per_unit) {
         below_total += hit.below;
         count = hit.count;
         last_bin = hit.bin;
+        if (r == 1 && lsh >= 10) {
+            // the normalised keys have no bits below the second digit (bracket narrower than 2^22 keys, the usual
+            // case): the 22-bit prefix IS the key, and its successor is the next non-empty bin of this round -- the
+            // third pass is only needed when that bin lies in another first-round bucket
+            if (hi < below_total + count) {
+                a_key = b_key = prefix;
+                resolved = true;
+            } else {
+                const uint32_t nb = block_next_nonempty<THREADS>(merged, round_bins(1), last_bin, scratch);
+                if (nb != 0xffffffffu) {
+                    a_key = prefix;
+                    b_key = (prefix & ~(round_mask(1) << round_shift(1))) | (nb << round_shift(1));
+                    resolved = true;
+                }
+            }
+        }
     }
-    uint32_t a_key = prefix, b_key = prefix;
-    if (!(hi < below_total + count)) {
+    if (!resolved) {
+        a_key = b_key = prefix;
+    }
+    if (!resolved && !(hi < below_total + count)) {
         const uint32_t nb = block_next_nonempty<THREADS>(merged, round_bins(2), last_bin, scratch);
         if (nb != 0xffffffffu) {
             b_key = (prefix & ~round_mask(2)) | nb;
