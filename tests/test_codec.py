@@ -173,3 +173,19 @@ def test_empty_streams(gold, tables):
     assert s == ro.encode_with_indexes([], [], *lists) and len(s) == 8
     assert codec.RansCoder().decode_with_indexes(s, empty, tables, None, None) == []
     assert codec.encode_streams(np.zeros((2, 0), np.int32), np.zeros((2, 0), np.int32), tables) == [s, s]
+
+
+def test_decoder_survives_garbage(tables):
+    """Corrupt / random streams must come back as an error or as some symbols -- never crash or hang."""
+    rng = np.random.default_rng(11)
+    c = codec.RansCoder()
+    idx = rng.integers(0, 64, size=500).astype(np.int32)
+    for k in range(200):
+        blob = rng.integers(0, 256, size=int(rng.integers(8, 400)) // 4 * 4, dtype=np.uint8).tobytes()
+        if k % 4 == 0:
+            blob = b"\xff" * len(blob)          # all-ones state: every escape counter saturates
+        try:
+            out = c.decode_with_indexes(blob, idx, tables, None, None)
+            assert len(out) == idx.size
+        except ValueError:
+            pass
