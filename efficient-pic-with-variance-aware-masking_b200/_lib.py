@@ -14,8 +14,8 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("PIC_LIB_PATH") or os.path.join(_PKG, "libpic_latent.so")   # override: kernel experiments
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_host.cu", "pic_rans.cpp")]
-_HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh")] + [
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_tma_select.cu", "pic_host.cu", "pic_rans.cpp")]
+_HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh", "pic_params.h")] + [
     os.path.join(_ROOT, "include", "pic_latent.h"), os.path.join(_ROOT, "include", "pic_codec.h")]
 
 PIC_OK = 0
@@ -29,7 +29,7 @@ Q_ONES = -1.0
 Q_ZEROS = 2.0
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
+              "-shared", "--threads", "0", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 _vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 _tables = [_vp, _i32, _i32, _vp, _vp]   # cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets (include/pic_codec.h)

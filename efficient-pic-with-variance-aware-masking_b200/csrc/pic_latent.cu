@@ -28,70 +28,11 @@
 #include "pic_math.cuh"
 #include "pic_fast.cuh"
 #include "pic_select.cuh"
+#include "pic_params.h"
 
 namespace pic {
 
-// ------------------------------------------------------------------------------------------
-// host-side helpers
-// ------------------------------------------------------------------------------------------
-static thread_local int g_last_cuda_error = 0;
-
-#define PIC_CUDA_CHECK(expr)                                   \
-    do {                                                       \
-        cudaError_t e__ = (expr);                              \
-        if (e__ != cudaSuccess) {                              \
-            pic::g_last_cuda_error = static_cast<int>(e__);    \
-            return PIC_ERR_CUDA;                               \
-        }                                                      \
-    } while (0)
-
-static int launch_status() {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        g_last_cuda_error = static_cast<int>(e);
-        return PIC_ERR_CUDA;
-    }
-    return PIC_OK;
-}
-
-static int sm_count() {
-    static int cached[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
-    }
-    return cached[dev];
-}
-
-static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static inline bool aligned4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
-
-constexpr int kFusedMaxElems = 131072;  // one CTA per unit up to here; larger units take the multi-CTA rounds path
-constexpr int kScratchWords = 192;  // block_select uses [0,48); small-set helpers [44,192)
-constexpr int kTableSmem = 64;
-constexpr int kHistWords = kHistBins + 8;  // [2048] = NaN count; rest padding
-constexpr int kApplyTile = 8192;           // elements per CTA in slice_apply_kernel
-constexpr int kWideThreads = 1024;         // latency variant of the select-only kernel (units <= SM count)
-constexpr int kRoundChunk = 16384;         // elements per CTA in hist_round_kernel
-constexpr int64_t kTwoKernelMinElems = int64_t(1) << 22;  // >= 4 Mi elements: select kernel + apply kernel
-constexpr int64_t kTwoKernelMinUnit = 32768;               // ... and units of at least this many elements
-
-struct SliceParams {
-    const float *y_top, *y_base, *mu, *std, *q01_per_unit, *thr_in, *noise, *table;
-    float q01, scale_bound, lik_bound;
-    int table_len;
-    int64_t n, units;
-    float *mask, *y_hat, *lik;
-    int32_t *idx, *symbols;
-    float *thr_out, *a_out, *b_out;
-    double *rate;
-    int apply_kind;  // 0: select only, 1: mask only, 2: full slice
-    int use_stage;   // dynamic shared memory holds the cp.async stage buffer
-    int repeat;      // select-only: `repeat` consecutive (virtual) units share one std block (multi-quality select)
-};
+thread_local int g_last_cuda_error = 0;
 
 // diagnostics: units whose sampled bracket missed (counted since library load)
 __device__ unsigned long long g_fallback_units = 0ull;
@@ -1256,6 +1197,13 @@ constexpr int64_t kMaxElemsPerLaunch = int64_t(1) << 33;
 
 template <bool TRAIN>
 static int launch_fused_f(const SliceParams &p, bool vec, cudaStream_t stream) {
+    if (p.apply_kind == 0 && vec) {
+        // select-only launches: measured choice between the three select kernels (scripts/select_tune.py)
+        static const int prefer_tma = [] { const char *e = getenv("PIC_PREFER_TMA"); return e ? atoi(e) : 0; }();
+        if (prefer_tma && select_tma_usable(p)) return launch_select_tma(p, stream);
+        if (select_lean_usable(p)) return launch_select_lean(p, stream);
+        if (select_tma_usable(p)) return launch_select_tma(p, stream);
+    }
     if (p.apply_kind == 0) return vec ? launch_fused_v<false, true, kOutsSelectOnly>(p, stream)
                                       : launch_fused_v<false, false, kOutsSelectOnly>(p, stream);
     if (!vec) return launch_fused_v<TRAIN, false, kOutsGeneric>(p, stream);
@@ -1563,6 +1511,7 @@ int pic_debug_select_counters(unsigned long long *sampled, unsigned long long *f
     PIC_CUDA_CHECK(cudaDeviceSynchronize());
     PIC_CUDA_CHECK(cudaMemcpyFromSymbol(sampled, g_sampled_units, sizeof(unsigned long long)));
     PIC_CUDA_CHECK(cudaMemcpyFromSymbol(fallback, g_fallback_units, sizeof(unsigned long long)));
+    select_tma_counters(sampled, fallback);
     return PIC_OK;
 }
 
