@@ -14,7 +14,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("PIC_LIB_PATH") or os.path.join(_PKG, "libpic_latent.so")   # override: kernel experiments
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_tma_select.cu", "pic_host.cu", "pic_rans.cpp")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_tma_select.cu", "pic_rank.cu", "pic_host.cu", "pic_rans.cpp")]
 _HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh", "pic_params.h")] + [
     os.path.join(_ROOT, "include", "pic_latent.h"), os.path.join(_ROOT, "include", "pic_codec.h")]
 
@@ -46,6 +46,8 @@ SIGNATURES = {
     "pic_select_threshold": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pic_select_threshold_multi": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp]),
     "pic_level_map": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "pic_rank_order_workspace_bytes": (_sz, [_i64, _i64]),
+    "pic_rank_order": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "pic_select_state_bytes": (_sz, [_i64]),
     "pic_hist_words": (_i64, []),
     "pic_select_begin": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),
@@ -103,11 +105,36 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: cannot build libpic_latent.so")
 
 
+STAMP_PATH = LIB_PATH + ".srchash"   # written next to the library by build(); travels with it, not committed
+
+
+def source_hash() -> str:
+    """SHA-256 over the compile flags and the bytes of every source / header of the library (sorted by name):
+    identifies the sources a binary was built from, independent of file times and of who built it."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(_SOURCES + _HEADERS):
+        if os.path.isfile(p):
+            h.update(os.path.basename(p).encode())
+            with open(p, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def built_from() -> str:
+    """The source hash recorded when the library on disk was built ('' if unknown)."""
+    try:
+        with open(STAMP_PATH) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def needs_build() -> bool:
-    if not os.path.isfile(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > t for p in _SOURCES + _HEADERS if os.path.isfile(p))
+    """True when the library is missing or was built from other sources than the ones on disk (hash, not mtime:
+    a binary that is newer than the sources but foreign to them is rebuilt too)."""
+    return not os.path.isfile(LIB_PATH) or built_from() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -121,6 +148,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
+    with open(STAMP_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     if verbose:
         print(res.stdout)
     return LIB_PATH

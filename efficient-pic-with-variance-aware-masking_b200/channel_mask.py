@@ -62,10 +62,20 @@ class ChannelMask(nn.Module):
         qualities.  Returns (level, thr): level [len(scale), ch, w, h] int32 with the first level that keeps
         each element (len(q_list) if none) -- ProgMask(q_l) - ProgMask(q_{l-1}) == (level == l), with
         q_{-1} = 0 -- and the thresholds thr [len(scale), len(q_list)]."""
+        if len(scale) == 0:
+            raise RuntimeError("stack expects a non-empty TensorList")
         blocks = [b if b.is_contiguous() else b.contiguous() for b in scale]
+        if not all(b.shape == blocks[0].shape for b in blocks):
+            raise RuntimeError("stack expects each tensor to be equal size")
         bs, ch, w, h = blocks[0].shape
         stacked = torch.cat([b.reshape(bs, ch * w * h) for b in blocks], dim=0)
-        thr = ops.select_threshold_multi(stacked, stacked.shape[0], list(q_list))
+        q_list = list(q_list)
+        if stacked.shape[1] <= ops.fused_max_elems():
+            thr = ops.select_threshold_multi(stacked, stacked.shape[0], q_list)
+        else:
+            # larger blocks (images beyond ~1024x1024): one large-unit select per level, as ProgMask does
+            thr = torch.stack([ops.select_threshold(stacked, stacked.shape[0], ops.pr_to_q01(q)) for q in q_list], dim=1)
+            thr = thr.contiguous()
         level = ops.level_map(stacked, thr, stacked.shape[0])
         return level.reshape(len(blocks) * bs, ch, w, h), thr
 
@@ -124,6 +134,13 @@ class ChannelMask(nn.Module):
         return torch.cat([m, m], dim=1) if mu_std else m
 
     # ------------------------------------------------------------------ extensions (not in the reference)
+    def rank_order(self, scale):
+        """Explicit variance-aware ranking per image: int32 [bs, ch*w*h] element indexes (NCHW, image-local) from the
+        most to the least uncertain, ties broken by ascending index.  `forward(scale, pr)` keeps exactly the first
+        `kept = #{scale >= quantile}` entries -- more than ceil(pr/10 * n) only when elements tie with the threshold
+        (the reference's `>=` keeps all of them)."""
+        return ops.rank_order(scale.contiguous(), scale.shape[0])
+
     def forward_multi(self, scale, prs):
         """One quality level per image/unit: `prs` is a sequence of len(scale) qualities or a
         prepared per-unit q01 tensor (ops.q01_tensor)."""

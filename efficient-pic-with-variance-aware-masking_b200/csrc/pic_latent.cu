@@ -1152,13 +1152,17 @@ static int launch_fused_t(const SliceParams &p_in, cudaStream_t stream) {
                             ? kSelectSmemBytes + (wide_select<THREADS, OUTS>() ? wide_park_bytes<THREADS>()
                                                   : (kSelectPipe && THREADS == 256 ? size_t(16384) : 0))
                             : fused_dyn_smem<TRAIN, THREADS>();
-    static bool configured = false;  // per instantiation
-    static int occ_blocks[2] = {0, 0};
-    if (!configured) {
+    // per instantiation AND per device: the attribute and the occupancy belong to the device that launches
+    static bool configured[64] = {false};
+    static int occ_blocks[64][2] = {{0}};
+    int dev = 0;
+    PIC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return PIC_ERR_INVALID_ARGUMENT;
+    if (!configured[dev]) {
         PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = true;
+        configured[dev] = true;
     }
-    int &occ = occ_blocks[p.use_stage];
+    int &occ = occ_blocks[dev][p.use_stage];
     if (occ == 0) {
         int q = 1;
         PIC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));

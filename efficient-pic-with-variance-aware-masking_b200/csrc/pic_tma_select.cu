@@ -1439,10 +1439,10 @@ bool select_lean_usable(const SliceParams &p) {
            aligned16(p.std) && p.units > 0;
 }
 
-int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
-    constexpr int CT = 256;
+template <int CT, int MINB>
+static int launch_lean_t(const SliceParams &p, cudaStream_t stream) {
     using L = LeanSmem<CT>;
-    auto kern = select_lean_kernel<CT, 4>;
+    auto kern = select_lean_kernel<CT, MINB>;
     int dev = 0;
     PIC_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return PIC_ERR_INVALID_ARGUMENT;
@@ -1470,6 +1470,19 @@ int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
     const int grid = static_cast<int>(p.units < max_grid ? p.units : max_grid);
     kern<<<grid, CT, smem, stream>>>(p, cfg);
     return launch_status();
+}
+
+int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
+    static const int ct = env_int("PIC_LEAN_CT", 0);
+    static const int minb = env_int("PIC_LEAN_MINB", 4);
+    // at most one unit per SM (per-slice launches, single images): wider CTAs finish each unit sooner
+    const bool few = p.units <= sm_count();
+    const int use = ct ? ct : (few ? 512 : 256);   // measured: 101 Kodak units 15.0 us (512) vs 17.0 (256, 1024)
+    if (use == 1024) return launch_lean_t<1024, 1>(p, stream);
+    if (use == 512) return launch_lean_t<512, 2>(p, stream);
+    if (minb == 5) return launch_lean_t<256, 5>(p, stream);
+    if (minb == 6) return launch_lean_t<256, 6>(p, stream);
+    return launch_lean_t<256, 4>(p, stream);
 }
 
 void select_tma_counters(unsigned long long *sampled, unsigned long long *fallback) {

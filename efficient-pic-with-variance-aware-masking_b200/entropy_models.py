@@ -108,6 +108,32 @@ class EntropyModel(nn.Module):
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
 
+    # ---- pickling / deepcopy (reference 103-110): the coder handle is stored by name --------------------
+    def __getstate__(self):
+        attributes = self.__dict__.copy()
+        attributes["entropy_coder"] = self.entropy_coder.name
+        attributes.pop("_tables_cache", None)     # host copy of the CDF tables: rebuilt on demand
+        attributes["_tables_gen_seen"] = None
+        return attributes
+
+    def __setstate__(self, state):
+        self.__dict__ = state
+        self.entropy_coder = _make_entropy_coder(self.__dict__.pop("entropy_coder"))
+
+    def _invalidate_tables(self) -> None:
+        """Called whenever the CDF buffers are replaced (update(), load_state_dict, .to()): the native coder's
+        host copy is keyed on a generation counter, not on the buffer's address (the allocator reuses blocks)."""
+        self._tables_gen = getattr(self, "_tables_gen", 0) + 1
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._invalidate_tables()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate_tables()
+        return out
+
     @property
     def offset(self):
         return self._offset
@@ -171,11 +197,11 @@ class EntropyModel(nn.Module):
 
     def _tables(self) -> "codec.CdfTables":
         """Host copy of the CDF tables for the native coder, rebuilt when update() replaces the buffers."""
-        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, self._quantized_cdf.numel())
-        if getattr(self, "_tables_key", None) != key:
+        gen = (getattr(self, "_tables_gen", 0), self._quantized_cdf._version)
+        if getattr(self, "_tables_gen_seen", None) != gen or getattr(self, "_tables_cache", None) is None:
             self._check_tables()
             self._tables_cache = codec.CdfTables(self._quantized_cdf, self._cdf_length, self._offset)
-            self._tables_key = key
+            self._tables_gen_seen = gen
         return self._tables_cache
 
     def _stream_lists(self):
@@ -329,6 +355,7 @@ class GaussianConditional(EntropyModel):
         self._quantized_cdf = table.to(device)
         self._offset = (-half_width).to(device)
         self._cdf_length = (support + 2).to(device)
+        self._invalidate_tables()
 
     # ---- hot path ---------------------------------------------------------------------------
     def _bounds(self) -> Tuple[float, float]:

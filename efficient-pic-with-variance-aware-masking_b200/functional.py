@@ -92,11 +92,27 @@ def progressive_slice_forward(y_top: torch.Tensor, y_base: Optional[torch.Tensor
     return out
 
 
+class _LogSum(torch.autograd.Function):
+    """sum(ln x) over the whole tensor as one kernel (f64 accumulation); d/dx = g / x, the gradient autograd
+    gives torch.log(x).sum() in the reference's loss (training/loss.py:45-60)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.log_sum(x, 1).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return (g.to(x.dtype) / x)
+
+
 def rate_bpp(likelihoods: torch.Tensor, num_pixels: int) -> torch.Tensor:
-    """training/loss.py:45-60: sum(log(lik)) / (-ln2 * num_pixels), as an f64 scalar tensor."""
+    """training/loss.py:45-60: sum(log(lik)) / (-ln2 * num_pixels), as an f64 scalar tensor; differentiable
+    with respect to the likelihoods (the rate term of the training loss)."""
     import math
 
-    total = ops.log_sum(likelihoods.contiguous(), 1).sum()
+    total = _LogSum.apply(likelihoods.contiguous())
     return total / (-math.log(2) * num_pixels)
 
 

@@ -20,8 +20,53 @@ QUANTIZE_MODES = {"noise": 0, "dequantize": 1, "symbols": 2, "ste": 3}
 
 
 # ----------------------------------------------------------------------------------- helpers
+import functools
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _tensors_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, dict):
+            for v in a.values():
+                if isinstance(v, torch.Tensor):
+                    yield v
+
+
+def _on_tensor_device(fn):
+    """Runs the wrapped op with the tensors' device current: the C ABI launches on the current device and
+    `_stream()` returns the current device's stream, so a module moved to cuda:1 while cuda:0 is current must
+    switch first.  All tensor arguments have to live on one device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for t in _tensors_of(args, kwargs):
+            if not t.is_cuda:
+                continue           # reported by _require with the op's own message
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"{fn.__name__}: all tensors must be on the same device, got {dev} and {t.device}")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def _expand_like(t: Optional[torch.Tensor], ref: torch.Tensor, name: str) -> Optional[torch.Tensor]:
+    """Broadcasts an operand to the shape of `ref` the way the reference's eager arithmetic does
+    (entropy_models.py:146-149, 161-168 accept means of shape [B, C, 1, 1])."""
+    if t is None or t.shape == ref.shape:
+        return t
+    try:
+        return t.expand_as(ref).contiguous()
+    except RuntimeError:
+        raise ValueError(f"{name} of shape {tuple(t.shape)} does not broadcast to {tuple(ref.shape)}") from None
 
 
 def _require(t: Optional[torch.Tensor], name: str, dtype=torch.float32) -> Optional[torch.Tensor]:
@@ -94,8 +139,23 @@ def _units_view(t: torch.Tensor, units: int) -> Tuple[int, int]:
     return units, total // units
 
 
-def _workspace(n_per_unit: int, units: int, device) -> Tuple[Optional[torch.Tensor], int]:
-    nbytes = int(lib().pic_workspace_bytes(n_per_unit, units))
+def workspace_bytes(n_per_unit: int, units: int) -> int:
+    """Scratch bytes the select needs for `units` units of n_per_unit elements (pic_workspace_bytes)."""
+    return int(lib().pic_workspace_bytes(n_per_unit, units))
+
+
+def _workspace(n_per_unit: int, units: int, device, workspace: Optional[torch.Tensor] = None
+               ) -> Tuple[Optional[torch.Tensor], int]:
+    """Caller-provided scratch (uint8 CUDA tensor, reusable across calls on one stream) or a fresh allocation."""
+    nbytes = workspace_bytes(n_per_unit, units)
+    if workspace is not None:
+        if not (workspace.is_cuda and workspace.dtype == torch.uint8 and workspace.is_contiguous()):
+            raise TypeError("workspace must be a contiguous CUDA uint8 tensor")
+        if workspace.device != torch.device(device):
+            raise RuntimeError("workspace must live on the tensors' device")
+        if workspace.numel() < nbytes:
+            raise ValueError(f"workspace holds {workspace.numel()} bytes, {nbytes} are needed (ops.workspace_bytes)")
+        return workspace, workspace.numel()
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     return ws, nbytes
 
@@ -121,7 +181,8 @@ def _q_args(q01, units, device):
 
 
 # ----------------------------------------------------------------------------------- select / mask
-def select_threshold(std: torch.Tensor, units: int, q01, want_ab: bool = False):
+@_on_tensor_device
+def select_threshold(std: torch.Tensor, units: int, q01, want_ab: bool = False, workspace: Optional[torch.Tensor] = None):
     """Exact torch.quantile per unit. Returns thr [units] (and a, b if want_ab)."""
     std = _require(std, "std")
     units, n = _units_view(std, units)
@@ -129,26 +190,29 @@ def select_threshold(std: torch.Tensor, units: int, q01, want_ab: bool = False):
     thr = torch.empty(units, dtype=torch.float32, device=std.device)
     a = torch.empty_like(thr) if want_ab else None
     b = torch.empty_like(thr) if want_ab else None
-    ws, ws_bytes = _workspace(n, units, std.device)
+    ws, ws_bytes = _workspace(n, units, std.device, workspace)
     check(lib().pic_select_threshold(_ptr(std), n, units, q, _ptr(qt), _ptr(thr), _ptr(a), _ptr(b),
                                      _ptr(ws), ws_bytes, _stream()), "pic_select_threshold")
     return (thr, a, b) if want_ab else thr
 
 
-def channel_mask(std: torch.Tensor, units: int, q01, want_thr: bool = False):
+@_on_tensor_device
+def channel_mask(std: torch.Tensor, units: int, q01, want_thr: bool = False, workspace: Optional[torch.Tensor] = None):
     """mask = (std >= quantile) as f32, same shape as std."""
     std = _require(std, "std")
     units, n = _units_view(std, units)
     q, qt = _q_args(q01, units, std.device)
     mask = torch.empty_like(std)
     thr = torch.empty(units, dtype=torch.float32, device=std.device) if want_thr else None
-    ws, ws_bytes = _workspace(n, units, std.device)
+    ws, ws_bytes = _workspace(n, units, std.device, workspace)
     check(lib().pic_channel_mask(_ptr(std), n, units, q, _ptr(qt), _ptr(mask), _ptr(thr), _ptr(ws), ws_bytes,
                                  _stream()), "pic_channel_mask")
     return (mask, thr) if want_thr else mask
 
 
-def attention_mask(std: torch.Tensor, units: int, q01, copies: int = 2, out: Optional[torch.Tensor] = None):
+@_on_tensor_device
+def attention_mask(std: torch.Tensor, units: int, q01, copies: int = 2, out: Optional[torch.Tensor] = None,
+                   workspace: Optional[torch.Tensor] = None):
     """REM attention mask: channel_mask written `copies` times along dim 1, shape [units, copies * C, ...]
     (torch.cat([m] * copies, 1) of the reference) from one select + one pass over std."""
     std = _require(std, "std")
@@ -159,12 +223,13 @@ def attention_mask(std: torch.Tensor, units: int, q01, copies: int = 2, out: Opt
         out = torch.empty(shape, dtype=torch.float32, device=std.device)
     elif out.numel() != units * copies * n or not out.is_contiguous():
         raise ValueError("out must be a contiguous tensor of units * copies * n elements")
-    ws, ws_bytes = _workspace(n, units, std.device)
+    ws, ws_bytes = _workspace(n, units, std.device, workspace)
     check(lib().pic_attention_mask(_ptr(std), n, units, q, _ptr(qt), copies, _ptr(out), None, _ptr(ws), ws_bytes,
                                    _stream()), "pic_attention_mask")
     return out
 
 
+@_on_tensor_device
 def select_threshold_multi(std: torch.Tensor, units: int, prs: Sequence[Number]) -> torch.Tensor:
     """Thresholds of every unit at every quality of `prs` in one launch. Returns thr [units, len(prs)]."""
     std = _require(std, "std")
@@ -177,6 +242,7 @@ def select_threshold_multi(std: torch.Tensor, units: int, prs: Sequence[Number])
     return thr
 
 
+@_on_tensor_device
 def level_map(std: torch.Tensor, thr: torch.Tensor, units: int) -> torch.Tensor:
     """level[e] = first l with std[e] >= thr[u, l] (or L): delta mask of level l == (level == l)."""
     std, thr = _require(std, "std"), _require(thr, "thr")
@@ -187,6 +253,20 @@ def level_map(std: torch.Tensor, thr: torch.Tensor, units: int) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
+def rank_order(std: torch.Tensor, units: int) -> torch.Tensor:
+    """Explicit ranking of every unit: unit-local element indexes sorted by (std descending, index ascending),
+    int32 [units, n].  The threshold mask's support is order[:, :kept] with kept = #{std >= thr}."""
+    std = _require(std, "std")
+    units, n = _units_view(std, units)
+    order = torch.empty((units, n), dtype=torch.int32, device=std.device)
+    nbytes = int(lib().pic_rank_order_workspace_bytes(n, units))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=std.device)
+    check(lib().pic_rank_order(_ptr(std), n, units, _ptr(order), _ptr(ws), nbytes, _stream()), "pic_rank_order")
+    return order
+
+
+@_on_tensor_device
 def mask_from_threshold(std: torch.Tensor, thr: torch.Tensor, units: int) -> torch.Tensor:
     std, thr = _require(std, "std"), _require(thr, "thr")
     units, n = _units_view(std, units)
@@ -197,9 +277,11 @@ def mask_from_threshold(std: torch.Tensor, thr: torch.Tensor, units: int) -> tor
 
 
 # ----------------------------------------------------------------------------------- fused slice
+@_on_tensor_device
 def slice_forward(y_top, y_base, mu, std, units: int, q01, scale_table: Optional[torch.Tensor] = None,
                   noise=None, thr_in=None, scale_bound: float = 0.11, lik_bound: float = 1e-9,
-                  want=("mask", "y_hat", "lik"), out: Optional[dict] = None) -> dict:
+                  want=("mask", "y_hat", "lik"), out: Optional[dict] = None,
+                  workspace: Optional[torch.Tensor] = None) -> dict:
     """One progressive slice for `units` units (see pic_slice_forward in include/pic_latent.h).
     want: subset of {mask, y_hat, lik, idx, symbols, thr, rate}.  `out` may carry preallocated
     output tensors (keys as in `want`) to avoid allocations in a steady-state loop."""
@@ -226,7 +308,7 @@ def slice_forward(y_top, y_base, mu, std, units: int, q01, scale_table: Optional
         res["thr"] = torch.empty(units, dtype=torch.float32, device=dev)
     if "rate" in want and "rate" not in res:
         res["rate"] = torch.empty(units, dtype=torch.float64, device=dev)
-    ws, ws_bytes = _workspace(n, units, dev)
+    ws, ws_bytes = _workspace(n, units, dev, workspace)
     check(lib().pic_slice_forward(
         _ptr(y_top), _ptr(y_base), _ptr(mu), _ptr(std), q, _ptr(qt), _ptr(thr_in), _ptr(noise),
         _ptr(table), 0 if table is None else table.numel(), scale_bound, lik_bound, n, units,
@@ -236,6 +318,7 @@ def slice_forward(y_top, y_base, mu, std, units: int, q01, scale_table: Optional
     return res
 
 
+@_on_tensor_device
 def slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, mask, noise=None, scale_bound: float = 0.11,
                    lik_bound: float = 1e-9, need_base: bool = True):
     """Returns (g_ytop, g_ybase or None, g_mu, g_std)."""
@@ -253,10 +336,12 @@ def slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, mask, noise=None, scal
 
 
 # ----------------------------------------------------------------------------------- un-fused ops
+@_on_tensor_device
 def gaussian_forward(inputs, scales, means=None, noise=None, likelihood_only: bool = False,
                      scale_bound: float = 0.11, lik_bound: float = 1e-9, want_outputs: bool = True):
     inputs, scales, means, noise = (_require(t, nm) for t, nm in
                                     ((inputs, "inputs"), (scales, "scales"), (means, "means"), (noise, "noise")))
+    scales, means, noise = (_expand_like(t, inputs, nm) for t, nm in ((scales, "scales"), (means, "means"), (noise, "noise")))
     outputs = torch.empty_like(inputs) if (want_outputs and not likelihood_only) else None
     lik = torch.empty_like(inputs)
     check(lib().pic_gaussian_forward(_ptr(inputs), _ptr(scales), _ptr(means), _ptr(noise), int(likelihood_only),
@@ -265,6 +350,7 @@ def gaussian_forward(inputs, scales, means=None, noise=None, likelihood_only: bo
     return outputs, lik
 
 
+@_on_tensor_device
 def gaussian_backward(g_out, g_lik, inputs, scales, means=None, noise=None, likelihood_only: bool = False,
                       scale_bound: float = 0.11, lik_bound: float = 1e-9):
     ts = [_require(t, nm) for t, nm in ((g_out, "g_out"), (g_lik, "g_lik"), (inputs, "inputs"), (scales, "scales"),
@@ -279,6 +365,7 @@ def gaussian_backward(g_out, g_lik, inputs, scales, means=None, noise=None, like
     return g_in, g_sc, g_mu
 
 
+@_on_tensor_device
 def build_indexes(scales, scale_table, scale_bound: float = 0.11) -> torch.Tensor:
     scales, scale_table = _require(scales, "scales"), _require(scale_table, "scale_table")
     idx = torch.empty(scales.shape, dtype=torch.int32, device=scales.device)
@@ -287,11 +374,13 @@ def build_indexes(scales, scale_table, scale_bound: float = 0.11) -> torch.Tenso
     return idx
 
 
+@_on_tensor_device
 def quantize(inputs, mode: str, means=None, noise=None, mask=None) -> torch.Tensor:
     if mode not in QUANTIZE_MODES:
         raise ValueError(f'Invalid quantization mode: "{mode}"')  # entropy_models.py:130-131
     inputs, means, noise, mask = (_require(t, nm) for t, nm in
                                   ((inputs, "inputs"), (means, "means"), (noise, "noise"), (mask, "mask")))
+    means, noise, mask = (_expand_like(t, inputs, nm) for t, nm in ((means, "means"), (noise, "noise"), (mask, "mask")))
     out_f = torch.empty_like(inputs) if mode != "symbols" else None
     out_i = torch.empty(inputs.shape, dtype=torch.int32, device=inputs.device) if mode == "symbols" else None
     check(lib().pic_quantize(_ptr(inputs), _ptr(means), _ptr(noise), _ptr(mask), inputs.numel(),
@@ -299,14 +388,16 @@ def quantize(inputs, mode: str, means=None, noise=None, mask=None) -> torch.Tens
     return out_i if mode == "symbols" else out_f
 
 
+@_on_tensor_device
 def dequantize(symbols, means=None) -> torch.Tensor:
     symbols = _require(symbols, "symbols", torch.int32)
-    means = _require(means, "means")
+    means = _expand_like(_require(means, "means"), symbols, "means")
     out = torch.empty(symbols.shape, dtype=torch.float32, device=symbols.device)
     check(lib().pic_dequantize(_ptr(symbols), _ptr(means), symbols.numel(), _ptr(out), _stream()), "pic_dequantize")
     return out
 
 
+@_on_tensor_device
 def log_sum(x, units: int) -> torch.Tensor:
     """Per-unit sum of ln(x) in f64 (numerator of training/loss.py:45-60)."""
     x = _require(x, "x")

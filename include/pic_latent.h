@@ -110,6 +110,19 @@ int pic_level_map(const float *std, const float *thr, int64_t n_per_unit, int64_
                   int32_t *level, pic_stream_t stream);
 
 /*
+ * (1b) Explicit variance-aware ranking (north_star step 1).  The reference has no ranking array: its mask is
+ * `std >= quantile` (layers/channel_mask.py:142-149), which keeps EVERY element tied with the threshold.  This
+ * entry exports the order itself under the stated tie-break: key (std descending, linear NCHW index within the unit
+ * ascending); -0 ties with +0, NaN ranks first (torch.sort's order).  order_out: [units][n_per_unit] int32, the
+ * unit-local element indexes from the most to the least uncertain.  Relation to (1)/(3): with
+ * kept = #{std >= thr}, the mask's support is exactly order[0 .. kept) -- kept >= ceil((1 - q01) n), with equality
+ * unless elements tie with the threshold.  ws: pic_rank_order_workspace_bytes().
+ */
+size_t pic_rank_order_workspace_bytes(int64_t n_per_unit, int64_t units);
+int pic_rank_order(const float *std, int64_t n_per_unit, int64_t units, int32_t *order_out, void *ws, size_t ws_bytes,
+                   pic_stream_t stream);
+
+/*
  * (1b) Split form of (1) for spatially tiled units (one image sharded over several GPUs,
  * SURVEY 8e).  Radix rounds r = 0,1,2 (11/11/10 key bits).  Per round every rank calls
  * pic_hist_round() on its local tile, all-reduces `hist` (uint32 sum, pic_hist_words() words

@@ -37,11 +37,22 @@ def unpack_mask(packed, shape):
     return np.unpackbits(packed)[:n].reshape(shape).astype(np.float32)
 
 
+# every likelihood comparison of the session: (test id, what, elements, worst relative error, elements that needed
+# the absolute floor, worst excess over the purely relative bound) -- printed by conftest.py at the end of the run so
+# that the use of LIK_ATOL is visible, not just allowed
+LIK_STATS = []
+
+
 def assert_lik_close(got, ref, what="lik"):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     err = np.abs(got - ref)
     tol = LIK_RTOL * np.abs(ref) + LIK_ATOL
+    if err.size:
+        rel = err / np.maximum(np.abs(ref), 1e-300)
+        over = err > LIK_RTOL * np.abs(ref)
+        LIK_STATS.append((os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], what, int(err.size),
+                          float(rel.max()), int(over.sum()), float((err - LIK_RTOL * np.abs(ref)).max())))
     bad = ~(err <= tol)
     assert not bad.any(), (f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst abs {err.max():.3e}, "
                            f"worst excess {(err - tol).max():.3e}")

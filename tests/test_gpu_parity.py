@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the golden vectors from the reference
 and against the C oracle on seeded inputs.  Bit-exact: masks, thresholds, indexes, symbols,
 y_hat.  Toleranced (see _common.py): likelihoods, rates, gradients."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -708,3 +710,144 @@ def test_randomised_slice_configurations(pic, dev):
             if k in want:
                 assert np.array_equal(N(out[k]), ref[k]), (k,) + tag
         assert_lik_close(N(out["lik"]), ref["lik"])
+
+
+# ------------------------------------------------------------------------------------------ round-2 additions
+def test_broadcast_means_like_the_reference(pic, dev):
+    """entropy_models.py:146-149, 161-168, 243-294: means of shape [B, C, 1, 1] broadcast against the inputs."""
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn((3, 8, 5, 7), device=dev, generator=g) * 4
+    means = torch.randn((3, 8, 1, 1), device=dev, generator=g)
+    gc = pic.GaussianConditional(None)
+    gc.scale_table = pic.get_scale_table()
+    gc = gc.to(dev)
+    sym = gc.quantize(x, "symbols", means)
+    assert torch.equal(sym, torch.round(x - means).int())
+    assert torch.equal(gc.quantize(x, "dequantize", means), torch.round(x - means) + means)
+    assert torch.equal(gc.dequantize(sym, means), sym.float() + means)
+    assert torch.equal(pic.ops.dequantize(sym, means), sym.float() + means)
+    with pytest.raises(ValueError, match="does not broadcast"):
+        pic.ops.dequantize(sym, means[:, :3])
+    # GaussianConditional.forward with broadcast scales and means
+    scales = torch.rand((3, 8, 1, 1), device=dev, generator=g) + 0.2
+    out, lik = gc(x, scales, means, training=False)
+    out2, lik2 = gc(x, scales.expand_as(x).contiguous(), means.expand_as(x).contiguous(), training=False)
+    assert torch.equal(out, out2) and torch.equal(lik, lik2)
+
+
+def test_rate_bpp_is_differentiable(pic, dev):
+    """training/loss.py:45-60: the rate term must send gradients back to the likelihoods."""
+    g = torch.Generator(device=dev).manual_seed(9)
+    lik = (torch.rand((2, 32, 16, 16), device=dev, generator=g) * 0.9 + 0.05).requires_grad_(True)
+    num_pixels = 2 * 256 * 256
+    bpp = pic.rate_bpp(lik, num_pixels)
+    ref_in = lik.detach().double().requires_grad_(True)
+    ref = torch.log(ref_in).sum() / (-np.log(2) * num_pixels)
+    assert abs(float(bpp.detach()) - float(ref.detach())) <= 1e-6 * abs(float(ref.detach()))   # f32 logs, f64 sum
+    bpp.backward()
+    ref.backward()
+    assert lik.grad is not None
+    np.testing.assert_allclose(N(lik.grad), N(ref_in.grad).astype(np.float32), rtol=2e-6)
+
+
+def test_proglevels_large_blocks_and_validation(pic, dev):
+    """ProgLevels on blocks above the fused select's size (a 1280x1280 image: 32 x 80 x 80 latents)."""
+    masking = pic.ChannelMask("point-based-std")
+    g = torch.Generator(device=dev).manual_seed(3)
+    blocks = [torch.exp(torch.randn((1, 32, 80, 80), device=dev, generator=g)) for _ in range(3)]
+    qs = [1.0, 2.5, 7.0]
+    level, thr = masking.ProgLevels(blocks, qs)
+    assert level.shape == (3, 32, 80, 80) and thr.shape == (3, 3)
+    prev = torch.zeros_like(level, dtype=torch.float32)
+    for l, q in enumerate(qs):
+        m = masking.ProgMask(blocks, q)
+        assert torch.equal((level == l).float(), m - prev)
+        prev = m
+    with pytest.raises(RuntimeError, match="non-empty"):
+        masking.ProgLevels([], qs)
+    with pytest.raises(RuntimeError, match="equal size"):
+        masking.ProgLevels([blocks[0], blocks[1][:, :16]], qs)
+
+
+def test_caller_workspace_and_device_guard(pic, dev):
+    std = T(trained_like(np.random.default_rng(21), (4, 49152))[3], dev)
+    want = pic.ops.select_threshold(std, 4, 0.5)
+    ws = torch.empty(pic.ops.workspace_bytes(49152, 4), dtype=torch.uint8, device=dev)
+    assert torch.equal(pic.ops.select_threshold(std, 4, 0.5, workspace=ws), want)
+    assert torch.equal(pic.ops.channel_mask(std, 4, 0.5, workspace=ws), (std >= want[:, None]).float())
+    with pytest.raises(ValueError, match="are needed"):
+        pic.ops.select_threshold(std, 4, 0.5, workspace=ws[:8])
+    if torch.cuda.device_count() >= 2:
+        # tensors on cuda:1 while cuda:0 is current: the op must switch device (and stream) by itself
+        other = torch.device("cuda:1")
+        std1 = std.to(other)
+        with torch.cuda.device(0):
+            thr1 = pic.ops.select_threshold(std1, 4, 0.5)
+            mask1 = pic.ops.channel_mask(std1, 4, 0.5)
+        assert thr1.device == other and torch.equal(thr1.cpu(), want.cpu())
+        assert torch.equal(mask1.cpu(), (std >= want[:, None]).float().cpu())
+        with pytest.raises(RuntimeError, match="same device"):
+            pic.ops.mask_from_threshold(std1, want, 4)
+
+
+@pytest.mark.parametrize("n", [32768, 49152, 65536, 131072, 5124, 20000])
+def test_select_kernels_agree(pic, dev, n):
+    """The three select kernels (lean, TMA-staged, legacy) give bit-identical thresholds and order statistics,
+    on iid, tie-heavy, mixed-sign, constant and NaN / inf units, at every quality incl. the open-ended ends."""
+    import subprocess
+    import sys as _sys
+    code = f"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))})
+import pic_b200
+from pic_b200 import ops
+dev = torch.device('cuda:0'); n = {n}; g = torch.Generator(device=dev).manual_seed(n)
+base = torch.exp(torch.randn((12, n), device=dev, generator=g) * 1.2 - 1.0)
+base[1] = torch.round(base[1] * 16) / 16
+base[2] = torch.randn(n, device=dev, generator=g) * 0.05
+base[3] = 0.25
+base[4, 17] = float('nan')
+base[5, 5] = float('inf'); base[5, 9] = -float('inf')
+base[6] = torch.round(base[6] * 2) / 2
+base[7, : n // 2] = 0.0
+prs = [1e-4, 0.02, 0.3, 0.5, 1.0, 2.5, 5.0, 7.3, 9.0, 9.97, 9.9999, 4.4]
+thr, a, b = ops.select_threshold(base, 12, ops.q01_tensor(prs, dev), want_ab=True)
+torch.cuda.synchronize()
+np.save(sys.argv[1], torch.stack([thr, a, b]).cpu().numpy())
+"""
+    import tempfile
+    outs = []
+    for env in ({}, {"PIC_PREFER_TMA": "1"}, {"PIC_LEAN_SELECT": "0", "PIC_TMA_SELECT": "0"}):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            subprocess.run([_sys.executable, "-c", code, f.name], check=True, env={**os.environ, **env}, timeout=300)
+            outs.append(np.load(f.name))
+    for other in outs[1:]:
+        assert np.array_equal(outs[0].view(np.uint32), other.view(np.uint32))
+
+
+def test_rank_order_export(pic, dev):
+    """Ranking by (std descending, linear index ascending) == numpy.lexsort; the threshold mask keeps a prefix of
+    it, longer than ceil(frac * n) only by the elements tied with the threshold."""
+    rng = np.random.default_rng(77)
+    n, units = 32 * 12 * 20, 5
+    std = trained_like(rng, (units, n))[3]
+    std[1] = np.round(std[1] * 8) / 8            # heavy ties
+    std[2, :100] = 0.0
+    std[2, 100:200] = -0.0                       # -0 ties with +0
+    std[3] = 0.5                                 # all equal
+    order = N(pic.ops.rank_order(T(std, dev), units))
+    assert order.dtype == np.int32 and order.shape == (units, n)
+    for u in range(units):
+        key = np.where(std[u] == 0, np.float32(0.0), std[u])         # canonical zero
+        want = np.lexsort((np.arange(n), -key.astype(np.float64)))
+        assert np.array_equal(order[u], want.astype(np.int32)), u
+    masking = pic.ChannelMask("point-based-std")
+    for pr in (1.0, 5.0, 7.3):
+        mask = N(masking(T(std.reshape(units, 32, 12, 20), dev), pr=pr)).reshape(units, n)
+        for u in range(units):
+            kept = int(mask[u].sum())
+            support = np.zeros(n, np.float32)
+            support[order[u, :kept]] = 1.0
+            assert np.array_equal(support, mask[u]), (pr, u)
+            thr = np.quantile(std[u].astype(np.float64), 1.0 - pr * 0.1)   # only to count the ties
+            assert kept >= int(np.ceil(pr * 0.1 * n)) - 1

@@ -156,3 +156,37 @@ def test_product_never_touches_the_oracle_or_the_reference():
     for f in os.listdir(os.path.join(ROOT, "tests")):
         if f.endswith(".py") and f != os.path.basename(__file__):   # this file names the path in the check above
             assert "/root/reference" not in open(os.path.join(ROOT, "tests", f)).read(), f
+
+
+def test_entropy_model_pickles_and_invalidates_its_table_cache():
+    """entropy_models.py:103-110 (coder stored by name) and the native coder's host copy of the CDF tables."""
+    import copy
+    import pickle
+
+    import pic_b200
+    from pic_b200 import codec
+
+    table = pic_b200.get_scale_table()
+    gc = pic_b200.GaussianConditional(None)
+    gc.update(table.tolist())
+    clone = copy.deepcopy(gc)
+    back = pickle.loads(pickle.dumps(gc))
+    for other in (clone, back):
+        assert type(other.entropy_coder) is type(gc.entropy_coder)
+        assert torch.equal(other._quantized_cdf, gc._quantized_cdf)
+    if isinstance(gc.entropy_coder, codec.RansCoder):
+        sym = torch.zeros((1, 64), dtype=torch.int32)
+        idx = torch.arange(64, dtype=torch.int32).reshape(1, 64)
+        first = gc.compress(sym, idx, already_quantize=True)
+        t1 = gc._tables()
+        assert gc._tables() is t1                                 # cached while nothing changes
+        gc.update((table * 1.5).tolist())                         # same-sized tables, new contents
+        assert gc._tables() is not t1                             # generation counter, not a pointer key
+        second = gc.compress(sym, idx, already_quantize=True)
+        fresh = pic_b200.GaussianConditional(None)
+        fresh.update((table * 1.5).tolist())
+        assert second == fresh.compress(sym, idx, already_quantize=True)
+        assert back.compress(sym, idx, already_quantize=True) == first
+        sd = fresh.state_dict()
+        gc.load_state_dict(sd)
+        assert gc._tables() is not t1
