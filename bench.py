@@ -5,24 +5,28 @@
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on host cores
     torchrun --nproc-per-node N bench.py --gpus N ...        # N>1: one rank per GPU
 
-Workloads (--workload):
-  kodak_sweep (default, BASELINE config[1]): Kodak-shape 768x512 latents ([1,32,32,48] => n=49152 per
-      unit), 10 progressive slices x 101-point quality sweep (pr = 0, 0.1, .. 10) = 1010 units per step,
-      codec outputs (mask, y_hat, likelihood, scale index).  One step = ONE launch of the fused kernel over
-      all 1010 (slice, quality) units (--launch per_slice: one launch per slice index).  Weak scaling:
-      every rank runs a full replica on its own data, no collective on the data path.
-  first_train (config[2]): [256,32,16,16] x 10 slices, random quality per image, training-mode forward
-      (noise) + fused backward.  Weak scaling, no collective.
-  rem_latent (config[3]): REM variant of the path at the first_train shape: 3 threshold selections per slice
-      (pre-REM attention mask duplicated to [B,64,h,w], checkpoint pass at q = 0.75, post-REM block mask) + slice.
-  tile8192 (config[4]): one 8192x8192 image, 10 slices of n=8388608, each rank holds a row band; the
-      per-slice threshold comes from NCCL all-reduced radix histograms.  Strong scaling.
-Inputs of one step are far larger than the 126 MB L2 (kodak_sweep: 794 MB), so consecutive steps stream
-from HBM without an explicit flush.  One JSON line is printed by rank 0 (keys: DESIGN.md "Measurement").
+The printed line measures `kodak_sweep` (BASELINE config[1]); its "workloads" block carries one record per other
+BASELINE configuration, measured in the same run (skip with --only-main):
+
+  kodak_sweep (headline): Kodak-shape 768x512 latents ([1,32,32,48] => n=49152 per unit), 10 progressive slices x
+      101-point quality sweep (pr = 0, 0.1, .. 10) = 1010 units per step with INDEPENDENT latents per unit, codec
+      outputs (mask, y_hat, likelihood, scale index).  One step = select launch + apply launch over all units.
+      Weak scaling: every rank runs a full replica on its own data, no collective on the data path.
+  per_slice: the same units in encoder order -- one select + one apply launch per slice index (10 dependent slices).
+  sweep_shared: the quality sweep as the reference runs it (check_levels_np): per slice ONE set of latents evaluated
+      at the 101 qualities (pic_slice_forward_multi: inputs cross HBM once, 16 B/element of output).
+  first_train (config[2]): [256,32,16,16] x 10 slices, random quality per image, training forward (noise) + backward.
+  rem_latent (config[3]): REM variant at the first_train shape: 3 threshold selections per slice (pre-REM attention
+      mask duplicated to [B,64,h,w], checkpoint pass at q = 0.75, post-REM block mask) + slice.
+  tile8192 (config[4]): one 8192x8192 image, 10 slices of n=8388608; at N > 1 each rank holds a row band and the
+      per-slice thresholds come from NCCL all-reduced radix histograms (strong scaling, a real collective).
+Inputs of one step are far larger than the 126 MB L2 (kodak_sweep: 794 MB), so consecutive steps stream from HBM
+without an explicit flush.  One JSON line is printed by rank 0 (keys: DESIGN.md "Measurement").
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -53,8 +57,8 @@ WORKLOADS = {
                        bytes_per_elem=4 + 8 + 4 + 32,  # star select + duplicated mask write, checkpoint select, slice fwd
                        ),
     "tile8192": dict(n=32 * 512 * 512, slices=10, prs=[1.0], scaling="strong",
-                     desc="single 8192x8192 image, 10 slices, q=1, row bands over the ranks, NCCL histogram all-reduce",
-                     bytes_per_elem=36,  # std read by the select rounds (>=1 pass from HBM) + the 32 of the apply
+                     desc="single 8192x8192 synthetic image, 10 slices, q=1, row bands over the ranks, NCCL histogram all-reduce",
+                     bytes_per_elem=36,  # std read by the select (>=1 pass from HBM) + the 32 of the apply
                      ),
 }
 METRIC = "mask+quantize+likelihood throughput"
@@ -167,47 +171,81 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_sample(wl, cores):
-    """Bounded sample of the workload for the CPU arm: same unit size, a few units per host thread."""
+def cpu_step_units(wl):
+    """Units of one CPU step: the WHOLE step of the CUDA arm (same units, same qualities), except for the
+    8M-element units of tile8192 (one unit is ~1 s of qsort)."""
     n = wl["n"]
     per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
     total = per_slice * wl["slices"]
-    sample_units = max(1, min(total, max(cores * 2, (4 << 20) // n)))
+    prs_slice = unit_prs(wl, per_slice, 4321)
     if n > (1 << 20):
-        sample_units = 1          # one 8M-element unit is ~1 s of qsort per pass
-    prs_all = unit_prs(wl, per_slice, 4321)
-    prs = [prs_all[u % len(prs_all)] for u in range(sample_units)]
-    return sample_units, prs
+        return 1, prs_slice[:1], total
+    return total, [prs_slice[u % per_slice] for u in range(total)], total
 
 
-def cpu_pass(po, wl, arrays, prs, table):
+def cpu_pass(po, arrays, prs, table):
     y_top, y_base, mu, std = arrays
     po.slice_forward(y_top, y_base, mu, std, prs, table, want=("mask", "y_hat", "lik", "idx"))
 
 
+def torch_reference_throughput(wl, seconds_budget):
+    """When PIC_REFERENCE_ROOT names a checkout of the reference (the build container; never the GPU box, where the
+    variable is unset and nothing is read) the reference's own torch functions are timed too: kind = "reference"."""
+    root = os.environ.get("PIC_REFERENCE_ROOT")
+    if not root or not os.path.isdir(root):
+        return None
+    try:
+        import torch
+        import ref_shim
+
+        if not ref_shim.reference_available():
+            return None
+        ref = ref_shim.load_reference()
+        torch.set_num_threads(host_threads())
+        n = wl["n"]
+        units = max(1, min(8, (1 << 21) // n))
+        hw = n // 32
+        arrays = [torch.from_numpy(a).reshape(units, 32, hw // 16, 16) for a in make_host_inputs(n, units, 99)]
+        masking, gc = ref.ChannelMask("point-based-std"), ref_shim.make_gaussian_conditional(ref)
+        t0 = time.perf_counter()
+        passes = 0
+        while time.perf_counter() - t0 < seconds_budget and passes < 20:
+            ref_shim.reference_slice_forward(ref, gc, masking, *arrays, 5.0)
+            passes += 1
+        dt = (time.perf_counter() - t0) / max(passes, 1)
+        return {"value": units * n / dt / 1e9, "unit": "Gelem/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{units} units x {n} elem through the reference's own torch functions ({passes} passes)"}
+    except Exception as exc:  # pragma: no cover - depends on the container
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def cpu_reference_throughput(wl, seconds_budget):
-    """Times the oracle port (oracle/pic_oracle.c, OpenMP over units) on a bounded sample."""
+    """Times the oracle port (oracle/pic_oracle.c, OpenMP over units) on the units of one full step."""
     import pic_oracle as po
 
     po.build()
     po.set_num_threads(host_threads())
     cores = po.num_threads()
     n = wl["n"]
-    sample_units, prs = cpu_sample(wl, cores)
-    arrays = make_host_inputs(n, sample_units, 99)
+    step_units, prs, total = cpu_step_units(wl)
+    arrays = make_host_inputs(n, step_units, 99)
     table = np.load(os.path.join(ROOT, "tests", "golden", "scale_table.npy"))
-    cpu_pass(po, wl, arrays, prs, table)  # warm-up
+    cpu_pass(po, arrays, prs, table)  # warm-up
     times, t_start = [], time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        cpu_pass(po, wl, arrays, prs, table)
+        cpu_pass(po, arrays, prs, table)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > seconds_budget or len(times) >= 50:
             break
     med = statistics.median(times)
-    return {"value": sample_units * n / med / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_units} units x {n} elem (forward, codec outputs), median of {len(times)} passes of "
-                      f"oracle/pic_oracle.c (qsort quantile + erfc + 63-step index), {cores} OpenMP threads"}
+    out = {"value": step_units * n / med / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
+           "sample": f"{step_units} of the step's {total} units x {n} elem (forward, codec outputs), median of {len(times)} "
+                     f"passes of oracle/pic_oracle.c (qsort quantile + erfc + 63-step index), {cores} OpenMP threads"}
+    tr = torch_reference_throughput(wl, 5.0)
+    if tr is not None:
+        out["torch_reference"] = tr
+    return out
 
 
 def run_reference(args, wl):
@@ -219,24 +257,28 @@ def run_reference(args, wl):
     po.set_num_threads(host_threads())
     cores = po.num_threads()
     n = wl["n"]
-    sample_units, prs = cpu_sample(wl, cores)
-    arrays = make_host_inputs(n, sample_units, 99)
+    step_units, prs, total = cpu_step_units(wl)
+    arrays = make_host_inputs(n, step_units, 99)
     table = np.load(os.path.join(ROOT, "tests", "golden", "scale_table.npy"))
-    for _ in range(args.warmup):
-        cpu_pass(po, wl, arrays, prs, table)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_pass(po, arrays, prs, table)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_pass(po, wl, arrays, prs, table)
+        cpu_pass(po, arrays, prs, table)
     dt = time.perf_counter() - t0
-    value = args.steps * sample_units * n / dt / 1e9
-    sample = (f"each step = {sample_units} units x {n} elem of the {args.workload} workload (forward, codec outputs) "
+    value = args.steps * step_units * n / dt / 1e9
+    slices = wl["slices"]
+    per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
+    sample = (f"each step = {step_units} of the {total} units x {n} elem of one {args.workload} step (forward, codec outputs) "
               f"through oracle/pic_oracle.c, the C port of the reference's torch CPU path (the reference is Python "
               f"and cannot travel to this box), {cores} OpenMP threads")
+    # same `config` keys as the CUDA arm (same workload, same units per step)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n,
-                                            "units_per_step": sample_units},
+            "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
+                                            "units_per_step_per_gpu": per_slice * slices,
+                                            "units_per_step": step_units, "elements_per_step": step_units * n},
             "cpu_baseline": {"value": value, "unit": "Gelem/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -244,340 +286,494 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
-def run_cuda(args, wl):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Per-process state of the CUDA arm."""
 
-    import pic_b200
-    from pic_b200 import distributed as pdist
-    from pic_b200 import ops
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. the NCCL version
-    # banner) is sent to stderr, the JSON line is written to the saved descriptor at the end.
-    sys.stdout.flush()
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    L = pic_b200.lib()
-    name = args.workload
-    n, slices = wl["n"], wl["slices"]
-    per_slice = len(wl["prs"]) if wl["prs"] is not None else wl.get("batch", 1)
-    units = per_slice * slices
-    prs = unit_prs(wl, per_slice, 4321 + rank)
-    seed = 1234 + 1000 * 2 + rank
-    table = pic_b200.get_scale_table().to(dev)
-    q_slice = ops.q01_tensor(prs, dev)
-    q_all = torch.cat([q_slice] * slices).contiguous()
-    import ctypes
+        import pic_b200
+        from pic_b200 import distributed as pdist
+        from pic_b200 import ops
 
-    def plan(n_, units_, needs_select=1):
+        self.torch, self.dist, self.pic, self.pdist, self.ops, self.args = torch, dist, pic_b200, pdist, ops, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU path)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.L = pic_b200.lib()
+        self.table = pic_b200.get_scale_table().to(self.dev)
+        self.hbm, self.peak_source = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def plan(self, n, units, needs_select=1):
         k = ctypes.c_int(0)
-        kind = L.pic_slice_forward_plan(n_, units_, needs_select, ctypes.byref(k))
+        kind = self.L.pic_slice_forward_plan(n, units, needs_select, ctypes.byref(k))
         return kind, k.value
 
-    fused = n <= int(L.pic_fused_max_elems())
-    launches = [0]
-    tile_comm = None
-    PLAN_KERNEL = {0: "slice_fused_kernel", 1: "slice_apply_kernel", 2: "slice_apply_kernel"}
-    main_kernel = "slice_fused_kernel"
+    def select_counters(self):
+        s, f = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        self.L.pic_debug_select_counters(ctypes.byref(s), ctypes.byref(f))
+        return int(s.value), int(f.value)
 
-    if name == "tile8192":
-        # strong scaling: the unit is split into `world` row bands; every rank owns one band of each slice
-        n_local = n // world
-        y_top, y_base, mu, std = make_device_inputs(torch, n_local, units, seed, dev)
-        want = ("mask", "y_hat", "lik", "idx")
-        outs = {k: torch.empty((units, n_local), dtype=torch.int32 if k == "idx" else torch.float32, device=dev)
-                for k in want}
-        backend = pdist.CudaTileBackend(std, units) if world > 1 else None
-        if world > 1 and not args.torch_collectives:
-            # collectives issued inside libpic_latent.so (one host call per select); checked once against the
-            # torch.distributed protocol: thresholds must be bit-identical
-            tile_comm = pdist.NcclTileComm(dev)
-            t_c = pdist.tiled_select_threshold(std, units, n, q_all, comm=tile_comm)
-            t_t = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
-            if not torch.equal(t_c, t_t):
-                raise RuntimeError("tiled select: library-issued NCCL path disagrees with the torch.distributed path")
-        main_kernel = "slice_apply_kernel" if (world == 1 or n_local > int(L.pic_fused_max_elems())) else "slice_fused_kernel"
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-        def step():
-            if world == 1:
-                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
-                launches[0] = plan(n, units)[1]   # pivot + sweep + cluster select + apply = 4
-            else:
-                thr = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend, comm=tile_comm)
-                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr, want=want, out=outs)
-                launches[0] = 9          # begin + 3 x (hist, advance) + finish + apply; + 4 NCCL all-reduces (not counted)
-        elems_per_rank = units * n_local
-        total_elems = units * n
-    elif name == "first_train":
-        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
-        g = torch.Generator(device=dev).manual_seed(seed + 7)
-        noise = torch.rand((units, n), device=dev, generator=g) - 0.5
-        g_lik = torch.randn((units, n), device=dev, generator=g)
-        g_yhat = torch.randn((units, n), device=dev, generator=g)
-        want = ("mask", "y_hat", "lik")
-        outs = {k: torch.empty((units, n), dtype=torch.float32, device=dev) for k in want}
+    def gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
 
-        fwd_kind, fwd_k = plan(n, units)
-        main_kernel = PLAN_KERNEL[fwd_kind]
 
-        def step():
-            ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)
-            ops.slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, outs["mask"], noise)
-            launches[0] = fwd_k + 1
-        elems_per_rank = units * n
-        total_elems = elems_per_rank * world
-    elif name == "rem_latent":
-        # models/rem_pic.py:181-195 (star mask on the pre-REM scale, duplicated for mu_std), 121-132 (checkpoint
-        # representation at quality_ref = 0.75 -> a second select), 382-391 (block mask on the refined scale + slice)
-        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
-        _, _, _, std_pre = make_device_inputs(torch, n, units, seed + 17, dev)
-        want = ("mask", "y_hat", "lik")
-        outs = {k: torch.empty((units, n), dtype=torch.float32, device=dev) for k in want}
-        att = torch.empty((units, 2, n), dtype=torch.float32, device=dev)
-        fwd_kind, fwd_k = plan(n, units)
-        main_kernel = PLAN_KERNEL[fwd_kind]
+def ev_time(torch, fn, reps=20):
+    """Average device time of fn over `reps` back-to-back calls (CUDA events on the current stream)."""
+    fn()
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(reps):
+        fn()
+    a1.record()
+    torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / reps
 
-        def step():
-            ops.attention_mask(std_pre, units, q_all, copies=2, out=att)  # pre-REM star mask, cat([m, m], 1)
-            ops.select_threshold(std_pre, units, ops.pr_to_q01(0.75))    # checkpoint pass threshold
-            ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs)
-            launches[0] = 3 + fwd_k                                      # select + mask pass, select, slice
-        elems_per_rank = units * n
-        total_elems = elems_per_rank * world
-    else:
-        y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, dev)
-        want = ("mask", "y_hat", "lik", "idx")
-        outs = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32, device=dev)
-                for k in want}
 
-        def view(t, s):
-            return t[s * per_slice:(s + 1) * per_slice]
-
-        step_kind, step_k = plan(n, units) if args.launch == "per_step" else plan(n, per_slice)
-        main_kernel = PLAN_KERNEL[step_kind]
-
-        def step():
-            if args.launch == "per_step":
-                ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, want=want, out=outs)
-                launches[0] = step_k
-            else:
-                for s in range(slices):
-                    o = {k: view(v, s) for k, v in outs.items()}
-                    ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice,
-                                      table, want=want, out=o)
-                launches[0] = slices * step_k
-        elems_per_rank = units * n
-        total_elems = elems_per_rank * world
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    warmup = max(args.warmup, 3)
-    for _ in range(warmup):
+def timed_steps(cx: Ctx, step, steps, warmup, graph=True, windows=5, sampler=None):
+    """W warm-up steps, then EXACTLY `steps` steps between barrier + synchronize (CUDA events, max over ranks);
+    then `windows` more windows of the same length for the spread.  The timed steps replay a CUDA graph of one step
+    when `graph` (the eager time of the same K steps is reported too)."""
+    torch = cx.torch
+    for _ in range(max(warmup, 3)):
         step()
-    barrier()
-    # The timed steps replay ONE step captured in a CUDA graph (the launch-bound loop: 2 launches / 0.3 ms), so that
-    # host scheduling of N processes on one box does not leak into a device measurement; the same K steps issued
-    # eagerly are timed first and reported as eager_ms_per_step.  NCCL steps (tiled, N > 1) stay eager.
+    cx.barrier()
     run_step, eager_ms = step, None
-    # (capturing the NCCL step was tried at N = 2: 2.5 % faster, but the process group then hangs at teardown)
-    use_graph = bool(args.graph) and not (name == "tile8192" and world > 1)
-    if use_graph:
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            step()
-        g1.record()
-        barrier()
-        eager_ms = g0.elapsed_time(g1) / args.steps
-        if world > 1:
-            t = torch.tensor([eager_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            eager_ms = float(t.item())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+    if graph:
+        eager_ms = cx.max_over_ranks(ev_time(torch, step, steps))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             step()
         for _ in range(3):
-            graph.replay()
-        run_step = graph.replay
-        barrier()
-    sampler = ClockSampler(local_rank, world)
-    if rank == 0:
+            g.replay()
+        run_step = g.replay
+        cx.barrier()
+    t_wall0 = time.perf_counter()
+    if sampler is not None and cx.rank == 0:
         sampler.start()
         time.sleep(0.1)
-    barrier()
+    cx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         run_step()
     ev1.record()
-    barrier()
+    cx.barrier()
     t_wall1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
-    rank_ms = [ms / args.steps]
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        every = [torch.zeros_like(tms) for _ in range(world)]
-        dist.all_gather(every, tms)
-        rank_ms = [float(t.item()) / args.steps for t in every]     # reported for transparency
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)                  # the step time is the slowest rank's
-        ms = float(tms.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    ms_per_step = ms / args.steps
-    value = total_elems / (ms_per_step * 1e-3) / 1e9
+    own_ms = ev0.elapsed_time(ev1) / steps
+    ms = cx.max_over_ranks(own_ms)
+    clocks = sampler.stop(t_wall0, t_wall1) if (sampler is not None and cx.rank == 0) else None
+    spread = []
+    for _ in range(windows):
+        cx.barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(steps):
+            run_step()
+        w1.record()
+        cx.barrier()
+        spread.append(cx.max_over_ranks(w0.elapsed_time(w1) / steps))
+    return {"ms": ms, "own_ms": own_ms, "eager_ms": eager_ms, "clocks": clocks,
+            "windows": {"n": windows, "steps_each": steps, "ms_per_step": [round(v, 5) for v in spread],
+                        "median": statistics.median(spread) if spread else None,
+                        "min": min(spread) if spread else None, "max": max(spread) if spread else None}}
 
-    # ---------------- end-to-end: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ---
+
+def roofline(cx: Ctx, name, kernel, kern_ms, per_launch_elems, kbytes, elems_per_rank, step_bytes_per_elem, ms_per_step,
+             other=None):
+    bytes_per_launch = per_launch_elems * kbytes
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name)
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "achieved": achieved, "peak": cx.hbm, "unit": "GB/s", "frac": achieved / cx.hbm,
+            "traffic": traffic, "peak_source": cx.peak_source, "kernel": kernel,
+            "algorithmic_bytes_per_elem": kbytes, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "launch_ms": kern_ms, "other_kernels": other,
+            "whole_step_frac": (elems_per_rank * step_bytes_per_elem / (ms_per_step * 1e-3) / 1e9) / cx.hbm}
+
+
+# ---- kodak_sweep (headline) + per_slice + sweep_shared -------------------------------------------------------------
+def bench_kodak(cx: Ctx, sampler):
+    torch, ops, args = cx.torch, cx.ops, cx.args
+    wl = WORKLOADS["kodak_sweep"]
+    n, slices = wl["n"], wl["slices"]
+    per_slice = len(wl["prs"])
+    units = per_slice * slices
+    seed = 1234 + 1000 * 2 + cx.rank
+    q_slice = ops.q01_tensor(unit_prs(wl, per_slice, 4321 + cx.rank), cx.dev)
+    q_all = torch.cat([q_slice] * slices).contiguous()
+    y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, cx.dev)
+    want = ("mask", "y_hat", "lik", "idx")
+    outs = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32, device=cx.dev) for k in want}
+    ws = torch.empty(ops.workspace_bytes(n, units), dtype=torch.uint8, device=cx.dev)
+    step_kind, step_k = cx.plan(n, units)
+
+    def step():
+        ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, want=want, out=outs, workspace=ws)
+
+    c0 = cx.select_counters()
+    t = timed_steps(cx, step, args.steps, args.warmup, graph=bool(args.graph), sampler=sampler)
+    c1 = cx.select_counters()
+    ms = t["ms"]
+    elems_per_rank, total_elems = units * n, units * n * cx.world
+    value = total_elems / (ms * 1e-3) / 1e9
+    # dominant kernel (apply, thresholds given) and the select kernel alone, CUDA events on this stream
+    thr0 = ops.select_threshold(std, units, q_all, workspace=ws)
+    apply_ms = ev_time(torch, lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, thr_in=thr0,
+                                                        want=want, out=outs, workspace=ws))
+    sel_ms = ev_time(torch, lambda: ops.select_threshold(std, units, q_all, workspace=ws))
+    other = {"select_kernel": "select_lean_kernel", "select_ms": sel_ms,
+             "select_GBps_of_std": units * n * 4 / (sel_ms * 1e-3) / 1e9, "select_frac_of_hbm": units * n * 4 / (sel_ms * 1e-3) / 1e9 / cx.hbm,
+             "apply_share_of_step": apply_ms / t["own_ms"]}
+    roof = roofline(cx, "kodak_sweep", "slice_apply_kernel", apply_ms, units * n, 32, elems_per_rank, 32, t["own_ms"], other)
+    per_rank = cx.gather({"rank": cx.rank, "seed": seed, "ms_per_step": round(t["own_ms"], 5), "select_ms": round(sel_ms, 5),
+                          "apply_ms": round(apply_ms, 5), "select_units_sampled": c1[0] - c0[0],
+                          "select_units_fallback": c1[1] - c0[1]})
+
+    # ---- end to end through host buffers (before the side workloads overwrite `outs`)
     e2e = None
-    if not args.no_e2e and name == "kodak_sweep":
-        chunk = args.e2e_chunk if args.e2e_chunk > 0 else max(1, min(per_slice, (48 << 20) // (n * 4)))
-        all_cpus = os.sched_getaffinity(0)
-        numa_node = None if args.no_numa_bind else ops.bind_host_to_device_numa(dev)   # pinned buffers local to the GPU
-        host_in = [t.cpu().pin_memory() for t in (y_top, y_base, mu, std)]
-        q_host = q_all.cpu().pin_memory()
-        host_out = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32).pin_memory()
-                    for k in want}
-        nbytes = int(L.pic_host_pipeline_bytes(n, chunk))
-        dbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        tb = table.cpu()
-        torch.cuda.synchronize()
+    if not args.no_e2e:
+        e2e = bench_e2e(cx, n, units, per_slice, (y_top, y_base, mu, std), q_all, outs, total_elems)
 
-        def host_step():
-            rc = L.pic_slice_forward_host(host_in[0].data_ptr(), host_in[1].data_ptr(), host_in[2].data_ptr(),
-                                          host_in[3].data_ptr(), 0.5, q_host.data_ptr(), None, tb.data_ptr(), 64,
-                                          0.11, 1e-9, n, units, chunk, host_out["mask"].data_ptr(),
-                                          host_out["y_hat"].data_ptr(), host_out["lik"].data_ptr(),
-                                          host_out["idx"].data_ptr(), None, None, None, dbuf.data_ptr(), nbytes)
-            if rc != 0:
-                raise RuntimeError(f"pic_slice_forward_host rc={rc}")
+    # ---- encoder order: one select + one apply launch per slice index
+    def view(tn, s):
+        return tn[s * per_slice:(s + 1) * per_slice]
 
-        host_step()
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        barrier()
+    ws_s = torch.empty(ops.workspace_bytes(n, per_slice), dtype=torch.uint8, device=cx.dev)
+
+    def step_per_slice():
+        for s in range(slices):
+            ops.slice_forward(view(y_top, s), view(y_base, s), view(mu, s), view(std, s), per_slice, q_slice, cx.table,
+                              want=want, out={k: view(v, s) for k, v in outs.items()}, workspace=ws_s)
+
+    extra = {}
+    if not args.only_main:
+        tp = timed_steps(cx, step_per_slice, max(5, args.steps // 2), 3, graph=bool(args.graph), windows=3)
+        _, ps_k = cx.plan(n, per_slice)
+        extra["per_slice"] = {
+            "desc": "kodak_sweep units in encoder order: 10 dependent slices, one select + one apply launch per slice (101 units each)",
+            "value": total_elems / (tp["ms"] * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": tp["ms"], "windows": tp["windows"],
+            "launches_per_step": slices * ps_k, "bytes_per_elem": 32,
+            "whole_step_frac": (elems_per_rank * 32 / (tp["own_ms"] * 1e-3) / 1e9) / cx.hbm, "scaling": "weak"}
+        # ---- the sweep on ONE set of latents per slice (what check_levels_np evaluates): inputs [slices, n]
+        yt1, yb1, mu1, sd1 = (view(a, 0)[:slices].contiguous() for a in (y_top, y_base, mu, std))
+        q_lv = torch.cat([q_slice] * 1).contiguous()
+        outs_m = {k: v.view(slices, per_slice, n) for k, v in outs.items()}
+        outs_m["thr"] = torch.empty((slices, per_slice), dtype=torch.float32, device=cx.dev)
+
+        def step_shared():
+            for s in range(slices):   # slices stay sequential (each slice's mu / std depend on the previous ones)
+                ops.slice_forward_multi(yt1[s:s + 1], yb1[s:s + 1], mu1[s:s + 1], sd1[s:s + 1], 1, wl["prs"], cx.table,
+                                        want=want, out={k: v[s:s + 1] for k, v in outs_m.items()}, q01_levels=q_lv)
+
+        tsd = timed_steps(cx, step_shared, max(5, args.steps // 2), 3, graph=bool(args.graph), windows=3)
+        extra["sweep_shared"] = {
+            "desc": "quality sweep of ONE set of Kodak latents per slice: 10 sequential slices x 101 qualities sharing the "
+                    "slice's inputs (pic_slice_forward_multi), codec outputs for every (slice, quality)",
+            "value": total_elems / (tsd["ms"] * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": tsd["ms"], "windows": tsd["windows"],
+            "launches_per_step": slices * 2, "bytes_per_elem": 16,
+            "whole_step_frac": (elems_per_rank * 16 / (tsd["own_ms"] * 1e-3) / 1e9) / cx.hbm, "scaling": "weak",
+            "note": "algorithmic bytes: 16 B/element of output; the shared inputs cross HBM once per slice"}
+
+    cfg = {"workload": "kodak_sweep", "desc": wl["desc"], "n_per_unit": n, "slices": slices,
+           "units_per_step_per_gpu": units, "elements_per_step": total_elems, "launch": "per_step",
+           "cuda_graph": bool(args.graph), "launches_per_step": step_k, "outputs": list(want), "bytes_per_elem": 32,
+           "l2": f"inputs of one step = {elems_per_rank * 16 / 1e6:.0f} MB per GPU > 126 MB L2, no explicit flush",
+           "parallelism": f"{cx.world} rank(s), units sharded, no collective"}
+    del y_top, y_base, mu, std, outs
+    torch.cuda.empty_cache()
+    return {"value": value, "ms": ms, "t": t, "roofline": roof, "per_rank": per_rank, "config": cfg, "extra": extra,
+            "e2e": e2e, "launches": step_k}
+
+
+def bench_e2e(cx: Ctx, n, units, per_slice, inputs, q_all, outs, total_elems):
+    """The same step through pic_slice_forward_host: pinned host buffers, H2D + kernels + D2H inside the timed region.
+    Two output formats: the API's f32 / i32 arrays, and compact u8 mask + u8 index (10 B/element back instead of 16)."""
+    torch, ops, args, L = cx.torch, cx.ops, cx.args, cx.L
+    chunk = args.e2e_chunk if args.e2e_chunk > 0 else max(1, min(per_slice, (48 << 20) // (n * 4)))
+    all_cpus = os.sched_getaffinity(0)
+    numa_node = None if args.no_numa_bind else ops.bind_host_to_device_numa(cx.dev)
+    host_in = [t.cpu().pin_memory() for t in inputs]
+    q_host = q_all.cpu().pin_memory()
+    want = ("mask", "y_hat", "lik", "idx")
+    host_out = {k: torch.empty((units, n), dtype=torch.int32 if k == "idx" else torch.float32).pin_memory() for k in want}
+    nbytes = int(L.pic_host_pipeline_bytes(n, chunk))
+    dbuf = torch.empty(nbytes, dtype=torch.uint8, device=cx.dev)
+    tb = cx.table.cpu()
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def run(fn):
+        fn()
+        cx.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            host_step()          # returns when the outputs are in host memory
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tdt = torch.tensor([dt], device=dev)
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-            dt = float(tdt.item())
-        e2e = {"value": total_elems * e2e_steps / dt / 1e9, "unit": "Gelem/s",
-               "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 16),
-               "steps": e2e_steps, "value_scope": "whole job (all ranks' elements / slowest rank's wall time)",
-               "bytes_scope": "per rank and step",
-               "host_numa_node": numa_node,
-               "api": "pic_slice_forward_host (C ABI, pinned host buffers, 3-slot copy/compute pipeline)"}
-        if rank == 0:
-            assert torch.equal(host_out["mask"][:per_slice], outs["mask"][:per_slice].cpu()), "host/device mismatch"
-        os.sched_setaffinity(0, all_cpus)   # the CPU baseline below gets every host core again
+            fn()          # returns when the outputs are in host memory
+        cx.barrier()
+        return cx.max_over_ranks(time.perf_counter() - t0)
 
-    # ---------------- roofline of the dominant kernel: CUDA events around that kernel alone ----------------
-    hbm, which = peaks()
-    roof = None
-    if rank == 0 or world > 1:
-        other = None
-        if name == "kodak_sweep" and args.launch == "per_step" and step_kind == 0:
-            kern_ms, per_launch_elems = ms_per_step, units * n       # the step IS one launch of the kernel
-        elif name == "kodak_sweep" and args.launch == "per_step":
-            # plan 1: select kernel + tile-ordered apply kernel.  Time the dominant (apply) kernel alone
-            # with the thresholds given, and the select kernel alone, with CUDA events on this stream.
-            def ev_time(fn, reps=20):
-                fn()
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(reps):
-                    fn()
-                a1.record()
-                torch.cuda.synchronize()
-                return a0.elapsed_time(a1) / reps
-            thr0 = ops.select_threshold(std, units, q_all)
-            kern_ms = ev_time(lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr0,
-                                                        want=want, out=outs))
-            sel_ms = ev_time(lambda: ops.select_threshold(std, units, q_all))
-            per_launch_elems = units * n
-            other = {"select_kernel": "slice_fused_kernel<select-only>", "select_ms": sel_ms,
-                     "select_GBps_of_std": units * n * 4 / (sel_ms * 1e-3) / 1e9,
-                     "apply_share_of_step": kern_ms / ms_per_step}
-        else:
-            reps = 10
-            if name == "first_train":
-                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs)  # noqa: E731
-                per_launch_elems = units * n
-            elif name == "rem_latent":
-                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs)  # noqa: E731
-                per_launch_elems = units * n
-            elif name == "tile8192":
-                thr0 = ops.select_threshold(std, units, q_all) if world == 1 else pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
-                fn = lambda: ops.slice_forward(y_top, y_base, mu, std, units, q_all, table, thr_in=thr0, want=want, out=outs)  # noqa: E731
-                per_launch_elems = elems_per_rank
-            else:
-                fn = lambda: ops.slice_forward(view(y_top, 0), view(y_base, 0), view(mu, 0), view(std, 0), per_slice, q_slice, table, want=want, out={k: view(v, 0) for k, v in outs.items()})  # noqa: E731
-                per_launch_elems = per_slice * n
-            fn()
-            torch.cuda.synchronize()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            for _ in range(reps):
-                fn()
-            k1.record()
-            torch.cuda.synchronize()
-            kern_ms = k0.elapsed_time(k1) / reps
-        kbytes = {"first_train": 32, "tile8192": 32, "rem_latent": 28}.get(name, wl["bytes_per_elem"])
-        bytes_per_launch = per_launch_elems * kbytes
-        achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
+    def host_step():
+        rc = L.pic_slice_forward_host(host_in[0].data_ptr(), host_in[1].data_ptr(), host_in[2].data_ptr(),
+                                      host_in[3].data_ptr(), 0.5, q_host.data_ptr(), None, tb.data_ptr(), 64,
+                                      0.11, 1e-9, n, units, chunk, host_out["mask"].data_ptr(),
+                                      host_out["y_hat"].data_ptr(), host_out["lik"].data_ptr(),
+                                      host_out["idx"].data_ptr(), None, None, None, dbuf.data_ptr(), nbytes)
+        if rc != 0:
+            raise RuntimeError(f"pic_slice_forward_host rc={rc}")
+
+    dt = run(host_step)
+    if cx.rank == 0:
+        assert torch.equal(host_out["mask"][:per_slice], outs["mask"][:per_slice].cpu()), "host/device mismatch"
+    # plain pinned copies of the same byte counts, both directions at once: the PCIe ceiling of this box
+    h2d_b, d2h_b = units * n * 16, units * n * 16
+    dsrc = torch.empty(h2d_b // 4, dtype=torch.float32, device=cx.dev)
+    hsrc = torch.empty(h2d_b // 4, dtype=torch.float32).pin_memory()
+    hdst = torch.empty(d2h_b // 4, dtype=torch.float32).pin_memory()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copies():
+        with torch.cuda.stream(s_in):
+            dsrc.copy_(hsrc, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hdst.copy_(dsrc, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    dt_copy = run(copies)
+    del dsrc, hsrc, hdst
+    e2e = {"value": total_elems * e2e_steps / dt / 1e9, "unit": "Gelem/s",
+           "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 16),
+           "steps": e2e_steps, "value_scope": "whole job (all ranks' elements / slowest rank's wall time)",
+           "bytes_scope": "per rank and step", "host_numa_node": numa_node,
+           "api": "pic_slice_forward_host (C ABI, pinned host buffers, 3-slot copy/compute pipeline)",
+           "pcie_copy_only": {"value": total_elems * e2e_steps / dt_copy / 1e9, "unit": "Gelem/s",
+                              "what": "cudaMemcpyAsync H2D || D2H of the same byte counts, no kernels (pinned, two streams)"},
+           "frac_of_copy_only": dt_copy / dt}
+    # compact outputs: u8 mask + u8 index
+    if hasattr(L, "pic_slice_forward_host_compact"):
+        hm = torch.empty((units, n), dtype=torch.uint8).pin_memory()
+        hi = torch.empty((units, n), dtype=torch.uint8).pin_memory()
+        nbytes_c = int(L.pic_host_pipeline_bytes(n, chunk))
+
+        def host_step_c():
+            rc = L.pic_slice_forward_host_compact(host_in[0].data_ptr(), host_in[1].data_ptr(), host_in[2].data_ptr(),
+                                                  host_in[3].data_ptr(), 0.5, q_host.data_ptr(), tb.data_ptr(), 64, 0.11, 1e-9,
+                                                  n, units, chunk, hm.data_ptr(), host_out["y_hat"].data_ptr(),
+                                                  host_out["lik"].data_ptr(), hi.data_ptr(), dbuf.data_ptr(), nbytes_c)
+            if rc != 0:
+                raise RuntimeError(f"pic_slice_forward_host_compact rc={rc}")
+
+        dtc = run(host_step_c)
+        if cx.rank == 0:
+            assert torch.equal(hm[:per_slice].float(), outs["mask"][:per_slice].cpu()), "compact mask mismatch"
+            assert torch.equal(hi[:per_slice].int(), outs["idx"][:per_slice].cpu()), "compact index mismatch"
+        e2e["compact"] = {"value": total_elems * e2e_steps / dtc / 1e9, "unit": "Gelem/s",
+                          "h2d_bytes_per_step": int(units * n * 16 + units * 4), "d2h_bytes_per_step": int(units * n * 10),
+                          "api": "pic_slice_forward_host_compact (u8 mask, u8 scale index, f32 y_hat / likelihood)"}
+    os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core again
+    return e2e
+
+
+# ---- first_train ---------------------------------------------------------------------------------------------------
+def bench_first_train(cx: Ctx):
+    torch, ops, args = cx.torch, cx.ops, cx.args
+    wl = WORKLOADS["first_train"]
+    n, slices, per_slice = wl["n"], wl["slices"], wl["batch"]
+    units = per_slice * slices
+    seed = 1234 + 1000 * 3 + cx.rank
+    q_all = torch.cat([ops.q01_tensor(unit_prs(wl, per_slice, 4321 + cx.rank), cx.dev)] * slices).contiguous()
+    y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, cx.dev)
+    g = torch.Generator(device=cx.dev).manual_seed(seed + 7)
+    noise = torch.rand((units, n), device=cx.dev, generator=g) - 0.5
+    g_lik = torch.randn((units, n), device=cx.dev, generator=g)
+    g_yhat = torch.randn((units, n), device=cx.dev, generator=g)
+    want = ("mask", "y_hat", "lik")
+    outs = {k: torch.empty((units, n), dtype=torch.float32, device=cx.dev) for k in want}
+    ws = torch.empty(ops.workspace_bytes(n, units), dtype=torch.uint8, device=cx.dev)
+    fwd_kind, fwd_k = cx.plan(n, units)
+
+    def fwd():
+        ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, noise=noise, want=want, out=outs, workspace=ws)
+
+    def step():
+        fwd()
+        ops.slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, outs["mask"], noise)
+
+    t = timed_steps(cx, step, max(5, args.steps // 2), 3, graph=False, windows=3)
+    fwd_ms = ev_time(torch, fwd, 10)
+    elems = units * n
+    rec = {"desc": wl["desc"], "value": elems * cx.world / (t["ms"] * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": t["ms"],
+           "windows": t["windows"], "launches_per_step": fwd_k + 1, "bytes_per_elem": wl["bytes_per_elem"], "scaling": "weak",
+           "whole_step_frac": (elems * wl["bytes_per_elem"] / (t["own_ms"] * 1e-3) / 1e9) / cx.hbm,
+           "forward_kernel": {"name": "slice_fused_kernel (training forward)", "ms": fwd_ms,
+                              "frac": (elems * 32 / (fwd_ms * 1e-3) / 1e9) / cx.hbm, "bytes_per_elem": 32},
+           "backward_kernel": {"name": "slice_backward_kernel", "ms": t["own_ms"] - fwd_ms,
+                               "frac": (elems * 48 / (max(t["own_ms"] - fwd_ms, 1e-6) * 1e-3) / 1e9) / cx.hbm, "bytes_per_elem": 48}}
+    del y_top, y_base, mu, std, noise, g_lik, g_yhat, outs
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ---- rem_latent ----------------------------------------------------------------------------------------------------
+def bench_rem(cx: Ctx):
+    torch, ops, args = cx.torch, cx.ops, cx.args
+    wl = WORKLOADS["rem_latent"]
+    n, slices, per_slice = wl["n"], wl["slices"], wl["batch"]
+    units = per_slice * slices
+    seed = 1234 + 1000 * 4 + cx.rank
+    q_all = torch.cat([ops.q01_tensor(unit_prs(wl, per_slice, 4321 + cx.rank), cx.dev)] * slices).contiguous()
+    # models/rem_pic.py:181-195 (star mask on the pre-REM scale, duplicated for mu_std), 121-132 (checkpoint
+    # representation at quality_ref = 0.75 -> a second select), 382-391 (block mask on the refined scale + slice)
+    y_top, y_base, mu, std = make_device_inputs(torch, n, units, seed, cx.dev)
+    _, _, _, std_pre = make_device_inputs(torch, n, units, seed + 17, cx.dev)
+    want = ("mask", "y_hat", "lik")
+    outs = {k: torch.empty((units, n), dtype=torch.float32, device=cx.dev) for k in want}
+    att = torch.empty((units, 2, n), dtype=torch.float32, device=cx.dev)
+    ws = torch.empty(ops.workspace_bytes(n, units), dtype=torch.uint8, device=cx.dev)
+    _, fwd_k = cx.plan(n, units)
+    q_ckpt = ops.pr_to_q01(0.75)
+
+    def fwd():
+        ops.slice_forward(y_top, y_base, mu, std, units, q_all, None, want=want, out=outs, workspace=ws)
+
+    def step():
+        ops.attention_mask(std_pre, units, q_all, copies=2, out=att, workspace=ws)   # pre-REM star mask, cat([m, m], 1)
+        ops.select_threshold(std_pre, units, q_ckpt, workspace=ws)                  # checkpoint pass threshold
+        fwd()
+
+    t = timed_steps(cx, step, max(5, args.steps // 2), 3, graph=False, windows=3)
+    fwd_ms = ev_time(torch, fwd, 10)
+    elems = units * n
+    rec = {"desc": wl["desc"], "value": elems * cx.world / (t["ms"] * 1e-3) / 1e9, "unit": "Gelem/s", "ms_per_step": t["ms"],
+           "windows": t["windows"], "launches_per_step": 3 + fwd_k, "bytes_per_elem": wl["bytes_per_elem"], "scaling": "weak",
+           "whole_step_frac": (elems * wl["bytes_per_elem"] / (t["own_ms"] * 1e-3) / 1e9) / cx.hbm,
+           "forward_kernel": {"name": "slice_fused_kernel (codec forward, 3 outputs)", "ms": fwd_ms,
+                              "frac": (elems * 28 / (fwd_ms * 1e-3) / 1e9) / cx.hbm, "bytes_per_elem": 28}}
+    del y_top, y_base, mu, std, std_pre, outs, att
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ---- tile8192 ------------------------------------------------------------------------------------------------------
+def bench_tile(cx: Ctx):
+    """One 8192x8192 image: N = 1 runs the large-unit select on one GPU; N > 1 splits every slice into row bands and
+    the thresholds come from the library-issued NCCL histogram all-reduces (a real collective on the data path)."""
+    torch, ops, pdist, args = cx.torch, cx.ops, cx.pdist, cx.args
+    wl = WORKLOADS["tile8192"]
+    n, units, world = wl["n"], wl["slices"], cx.world
+    n_local = n // world
+    seed = 1234 + 1000 * 5 + cx.rank
+    q_all = ops.q01_tensor([1.0] * units, cx.dev)
+    y_top, y_base, mu, std = make_device_inputs(torch, n_local, units, seed, cx.dev)
+    want = ("mask", "y_hat", "lik", "idx")
+    outs = {k: torch.empty((units, n_local), dtype=torch.int32 if k == "idx" else torch.float32, device=cx.dev) for k in want}
+    rec = {"desc": wl["desc"], "unit": "Gelem/s", "bytes_per_elem": wl["bytes_per_elem"], "scaling": "strong",
+           "n_per_unit": n, "n_local_per_rank": n_local}
+    comm = None
+    if world == 1:
+        ws = torch.empty(ops.workspace_bytes(n, units), dtype=torch.uint8, device=cx.dev)
+
+        def step():
+            ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, want=want, out=outs, workspace=ws)
+        rec["launches_per_step"] = cx.plan(n, units)[1]
+        rec["collectives_per_step"] = 0
+        graph = bool(args.graph)
+    else:
+        backend = pdist.CudaTileBackend(std, units)
+        comm = pdist.NcclTileComm(cx.dev)
+        t_c = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm)
+        t_t = pdist.tiled_select_threshold(std, units, n, q_all, backend=backend)
+        same = bool(torch.equal(t_c, t_t))
+        every = [torch.zeros_like(t_c) for _ in range(world)]
+        cx.dist.all_gather(every, t_c)
+        same_ranks = all(bool(torch.equal(every[0], e)) for e in every)
+        rec["thresholds_equal"] = {"library_nccl_vs_torch_distributed": same, "across_ranks": same_ranks}
+
+        def step():
+            thr = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm)
+            ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, thr_in=thr, want=want, out=outs)
+        rec["launches_per_step"] = 9
+        rec["collectives_per_step"] = comm.collectives_per_select if hasattr(comm, "collectives_per_select") else 4
+        rec["collective"] = "ncclAllReduce(uint32 sum) of the per-slice radix histograms + ncclAllReduce(min), issued by libpic_latent.so"
+        graph = False
+    t = timed_steps(cx, step, max(5, args.steps // 2), 3, graph=graph, windows=3)
+    rec.update({"value": units * n / (t["ms"] * 1e-3) / 1e9, "ms_per_step": t["ms"], "windows": t["windows"],
+                "ms_per_step_by_rank": [round(v, 5) for v in cx.gather(t["own_ms"])],
+                "whole_step_frac": (units * n_local * wl["bytes_per_elem"] / (t["own_ms"] * 1e-3) / 1e9) / cx.hbm})
+    if comm is not None:
+        comm.close()
+    del y_top, y_base, mu, std, outs
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_cuda(args):
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. the NCCL version banner) is sent
+    # to stderr, the JSON line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    cx = Ctx(args)
+    sampler = ClockSampler(cx.local_rank, cx.world)
+    main = bench_kodak(cx, sampler)
+    workloads = dict(main["extra"])
+    if not args.only_main:
+        for name, fn in (("first_train", bench_first_train), ("rem_latent", bench_rem), ("tile8192", bench_tile)):
             try:
-                traffic = json.load(open(tpath)).get(name)
-            except Exception:
-                traffic = None
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": traffic, "peak_source": which, "kernel": main_kernel,
-                "algorithmic_bytes_per_elem": kbytes, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "launch_ms": kern_ms, "other_kernels": other,
-                "whole_step_frac": (elems_per_rank * wl["bytes_per_elem"] / (ms_per_step * 1e-3) / 1e9) / hbm}
-    if tile_comm is not None:
-        tile_comm.close()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+                workloads[name] = fn(cx)
+            except Exception as exc:  # a failing side workload must not take the headline down
+                workloads[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                cx.torch.cuda.empty_cache()
+    if cx.rank != 0:
+        if cx.world > 1:
+            cx.dist.destroy_process_group()
         return
+    wl = WORKLOADS["kodak_sweep"]
     cpu = None if args.no_cpu else cpu_reference_throughput(wl, args.cpu_seconds)
+    t = main["t"]
     line = {
-        "metric": METRIC, "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "ms_per_step_by_rank": [round(t, 5) for t in rank_ms],
-        "eager_ms_per_step": eager_ms,
-        "config": {"workload": name, "desc": wl["desc"], "n_per_unit": n, "slices": slices,
-                   "units_per_step_per_gpu": units, "elements_per_step": total_elems, "launch": args.launch,
-                   "cuda_graph": use_graph,
-                   "launches_per_step": launches[0], "outputs": list(want), "bytes_per_elem": wl["bytes_per_elem"],
-                   "l2": f"inputs of one step = {elems_per_rank * 16 / 1e6:.0f} MB per GPU > 126 MB L2, no explicit flush",
-                   "parallelism": (f"{world} rank(s), row-band tiles + NCCL histogram all-reduce"
-                                   + (" issued by libpic_latent.so" if tile_comm is not None else " over torch.distributed")
-                                   if name == "tile8192"
-                                   else f"{world} rank(s), units sharded, no collective")},
-        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
+        "metric": METRIC, "value": main["value"], "unit": "Gelem/s", "n_gpus": cx.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": main["ms"], "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step_by_rank": [r["ms_per_step"] for r in main["per_rank"]], "per_rank": main["per_rank"],
+        "windows": t["windows"], "eager_ms_per_step": t["eager_ms"], "config": main["config"],
+        "roofline": main["roofline"], "cpu_baseline": cpu, "e2e": main["e2e"],
+        "gpu_launches": main["launches"] * args.steps, "clocks": t["clocks"], "workloads": workloads,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 def main():
@@ -586,12 +782,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS))
-    ap.add_argument("--launch", default="per_step", choices=["per_step", "per_slice"],
-                    help="kodak_sweep: all (slice, q) units of a step in one launch, or one launch per slice index")
+    ap.add_argument("--workload", default="kodak_sweep", choices=sorted(WORKLOADS),
+                    help="reference arm: which configuration the CPU path runs (the CUDA arm always prints kodak_sweep "
+                         "with the other configurations in its `workloads` block)")
+    ap.add_argument("--only-main", action="store_true", help="skip the `workloads` block")
     ap.add_argument("--graph", type=int, default=1, help="1: timed steps replay a CUDA graph of one step (default; NCCL steps stay eager)")
-    ap.add_argument("--torch-collectives", action="store_true",
-                    help="tile8192, N > 1: carry the histogram all-reduces over torch.distributed instead of the library's own NCCL calls")
     ap.add_argument("--no-numa-bind", action="store_true", help="e2e: do not bind the process to the GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -599,11 +794,10 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=0, help="units per pipeline chunk of the host-buffer path (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_cuda(args, wl)
+        run_cuda(args)
 
 
 if __name__ == "__main__":

@@ -68,6 +68,8 @@ SIGNATURES = {
     "pic_mask_from_threshold": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "pic_slice_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _f32,
                                     _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pic_slice_forward_multi": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _f32, _f32, _i64, _i64,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pic_slice_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64,
                                      _vp, _vp, _vp, _vp, _vp]),
     "pic_gaussian_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
@@ -87,6 +89,8 @@ SIGNATURES = {
     "pic_rans_encode_levels": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32] + _tables + [_vp, _i64, _vp, _i32]),
     "pic_rans_decode_levels": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32] + _tables + [_vp, _i32]),
     "pic_host_pipeline_bytes": (_sz, [_i64, _i64]),
+    "pic_slice_forward_host_compact": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _f32, _f32, _i64, _i64, _i64,
+                                                 _vp, _vp, _vp, _vp, _vp, _sz]),
     "pic_slice_forward_host": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _f32, _f32,
                                          _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
 }

@@ -112,7 +112,10 @@ __host__ __device__ inline int outs_of(const SliceParams &p) {
 template <bool TRAIN, bool VEC, int THREADS, int OUTS>
 __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, int len,
                                              const uint32_t *keys, int mode, float thr_in,
-                                             const IndexCtx &ic, float4 *stage = nullptr) {
+                                             const IndexCtx &ic, float4 *stage = nullptr, int64_t in_off = -1) {
+    // in_off: element offset of the INPUTS when it differs from the outputs' (multi-quality apply: `repeat`
+    // consecutive output units share one input unit)
+    if (in_off < 0) in_off = off;
     float rate_acc = 0.0f;
     const int tid = threadIdx.x;
     const bool full = p.apply_kind == 2;
@@ -127,11 +130,12 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
         const uint64_t pol_first = policy_evict_first();
         // one 32-bit vector index for every tensor (host guarantees total elements < 2^34)
         const uint32_t vbase = static_cast<uint32_t>(off >> 2);
-        const float4 *std4 = reinterpret_cast<const float4 *>(p.std);
-        const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top);
-        const float4 *yb4 = reinterpret_cast<const float4 *>(p.y_base);
-        const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu);
-        const float4 *nz4 = reinterpret_cast<const float4 *>(p.noise);
+        const uint32_t vin = static_cast<uint32_t>(in_off >> 2);
+        const float4 *std4 = reinterpret_cast<const float4 *>(p.std) + vin - vbase;   // inputs are indexed with vi too
+        const float4 *yt4 = reinterpret_cast<const float4 *>(p.y_top) + vin - vbase;
+        const float4 *yb4 = reinterpret_cast<const float4 *>(p.y_base) + vin - vbase;
+        const float4 *mu4 = reinterpret_cast<const float4 *>(p.mu) + vin - vbase;
+        const float4 *nz4 = reinterpret_cast<const float4 *>(p.noise) + vin - vbase;
         const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
         // Software pipeline: with a stage buffer the inputs of iteration i+1 are copied
         // global->shared (cp.async, per-thread private 16-byte slots: no barrier needed) while
@@ -211,15 +215,15 @@ __device__ __forceinline__ float apply_range(const SliceParams &p, int64_t off, 
         if (piped) cp_async_wait<0>();
     } else {
         for (int j = tid; j < len; j += THREADS) {
-            const float sv = keys ? key_to_float(keys[j]) : __ldg(p.std + off + j);
+            const float sv = keys ? key_to_float(keys[j]) : __ldg(p.std + in_off + j);
             if (!full) {
                 p.mask[off + j] = ((sv >= thr) || force_one) ? 1.0f : 0.0f;
                 continue;
             }
-            const float ytv = __ldg(p.y_top + off + j);
-            const float ybv = has_base ? __ldg(p.y_base + off + j) : 0.0f;
-            const float muv = __ldg(p.mu + off + j);
-            const float nzv = TRAIN ? __ldg(p.noise + off + j) : 0.0f;
+            const float ytv = __ldg(p.y_top + in_off + j);
+            const float ybv = has_base ? __ldg(p.y_base + in_off + j) : 0.0f;
+            const float muv = __ldg(p.mu + in_off + j);
+            const float nzv = TRAIN ? __ldg(p.noise + in_off + j) : 0.0f;
             const float s[2] = {sv, sv}, yt[2] = {ytv, ytv}, yb[2] = {ybv, ybv}, mu[2] = {muv, muv}, nz[2] = {nzv, nzv};
             PairOut o;
             apply_pair<TRAIN>(s, yt, yb, mu, nz, has_base, thr, force_one, p.scale_bound, p.lik_bound, want_lik,
@@ -728,7 +732,10 @@ __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, i
     if (tile == 0 && tid == 0 && p.thr_out) p.thr_out[u] = thr;
     const int64_t begin = static_cast<int64_t>(tile) * kApplyTile;
     const int len = static_cast<int>(min(static_cast<int64_t>(kApplyTile), p.n - begin));
-    const float acc = apply_range<TRAIN, VEC, THREADS, OUTS>(p, u * p.n + begin, len, nullptr, mode, thr, ic);
+    // multi-quality apply: `repeat` consecutive output units (one per quality level) read the same input unit
+    const int64_t u_in = (p.repeat > 1) ? u / p.repeat : u;
+    const float acc = apply_range<TRAIN, VEC, THREADS, OUTS>(p, u * p.n + begin, len, nullptr, mode, thr, ic, nullptr,
+                                                             u_in * p.n + begin);
     if (p.rate) {
         const double total = block_sum_f64<THREADS>(acc, red);
         if (tid == 0) atomicAdd(&p.rate[u], total);
@@ -1843,6 +1850,35 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
         if (rc != PIC_OK) return rc;
         p.thr_in = w.thr;
     }
+    return launch_apply(p, stream);
+}
+
+int pic_slice_forward_multi(const float *y_top, const float *y_base, const float *mu, const float *std,
+                            const float *q01_levels, int levels, const float *scale_table, int table_len,
+                            float scale_bound, float lik_bound, int64_t n_per_unit, int64_t units, float *mask,
+                            float *y_hat, float *lik, int32_t *idx, int32_t *symbols, float *thr_out, double *rate,
+                            pic_stream_t stream_) {
+    int rc = check_common(n_per_unit, units);
+    if (rc != PIC_OK) return rc;
+    if (!y_top || !mu || !std || !q01_levels || !thr_out || levels < 1) return PIC_ERR_INVALID_ARGUMENT;
+    if (idx && (!scale_table || table_len < 1)) return PIC_ERR_INVALID_ARGUMENT;
+    if (!(scale_bound > 0.0f)) return PIC_ERR_INVALID_ARGUMENT;
+    if (n_per_unit > kFusedMaxElems) return PIC_ERR_TOO_LARGE;   // larger units: one pic_slice_forward per level
+    if (units * static_cast<int64_t>(levels) * n_per_unit > kMaxElemsPerLaunch) return PIC_ERR_TOO_LARGE;
+    const void *ptrs[] = {y_top, y_base, mu, std, mask, y_hat, lik, idx, symbols};
+    for (const void *q : ptrs)
+        if (q && !aligned4(q)) return PIC_ERR_UNALIGNED;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    rc = pic_select_threshold_multi(std, n_per_unit, units, q01_levels, levels, thr_out, stream_);
+    if (rc != PIC_OK) return rc;
+    SliceParams p{};
+    p.y_top = y_top; p.y_base = y_base; p.mu = mu; p.std = std;
+    p.q01_per_unit = q01_levels; p.thr_in = thr_out;
+    p.table = scale_table; p.table_len = table_len;
+    p.scale_bound = scale_bound; p.lik_bound = lik_bound;
+    p.n = n_per_unit; p.units = units * levels; p.repeat = levels;
+    p.mask = mask; p.y_hat = y_hat; p.lik = lik; p.idx = idx; p.symbols = symbols; p.rate = rate;
+    p.apply_kind = 2;
     return launch_apply(p, stream);
 }
 

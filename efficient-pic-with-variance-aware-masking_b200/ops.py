@@ -319,6 +319,42 @@ def slice_forward(y_top, y_base, mu, std, units: int, q01, scale_table: Optional
 
 
 @_on_tensor_device
+def slice_forward_multi(y_top, y_base, mu, std, units: int, prs: Sequence[Number], scale_table=None,
+                        scale_bound: float = 0.11, lik_bound: float = 1e-9, want=("mask", "y_hat", "lik"),
+                        out: Optional[dict] = None, q01_levels: Optional[torch.Tensor] = None) -> dict:
+    """Quality sweep of one set of latents (pic_slice_forward_multi): every output is [units, len(prs), n]; the
+    `len(prs)` qualities of a unit share its inputs.  `q01_levels` may carry a prepared [units, levels] q01 tensor."""
+    y_top, y_base, mu, std = (_require(t, nm) for t, nm in
+                              ((y_top, "y_top"), (y_base, "y_base"), (mu, "mu"), (std, "std")))
+    units, n = _units_view(std, units)
+    levels = len(prs)
+    q = _require(q01_levels, "q01_levels") if q01_levels is not None else q01_tensor(list(prs) * units, std.device)
+    if q.numel() != units * levels:
+        raise ValueError("q01_levels must hold units * levels values")
+    table = _require(scale_table, "scale_table") if "idx" in want else None
+    if "idx" in want and table is None:
+        raise ValueError("scale_table is required for idx")
+    res = dict(out) if out else {}
+    dev, shape = std.device, (units, levels, n)
+    for k in ("mask", "y_hat", "lik"):
+        if k in want and k not in res:
+            res[k] = torch.empty(shape, dtype=torch.float32, device=dev)
+    for k in ("idx", "symbols"):
+        if k in want and k not in res:
+            res[k] = torch.empty(shape, dtype=torch.int32, device=dev)
+    if "thr" not in res:
+        res["thr"] = torch.empty((units, levels), dtype=torch.float32, device=dev)
+    if "rate" in want and "rate" not in res:
+        res["rate"] = torch.empty((units, levels), dtype=torch.float64, device=dev)
+    check(lib().pic_slice_forward_multi(
+        _ptr(y_top), _ptr(y_base), _ptr(mu), _ptr(std), _ptr(q), levels, _ptr(table),
+        0 if table is None else table.numel(), scale_bound, lik_bound, n, units,
+        _ptr(res.get("mask")), _ptr(res.get("y_hat")), _ptr(res.get("lik")), _ptr(res.get("idx")),
+        _ptr(res.get("symbols")), _ptr(res["thr"]), _ptr(res.get("rate")), _stream()), "pic_slice_forward_multi")
+    return res
+
+
+@_on_tensor_device
 def slice_backward(g_lik, g_yhat, y_top, y_base, mu, std, mask, noise=None, scale_bound: float = 0.11,
                    lik_bound: float = 1e-9, need_base: bool = True):
     """Returns (g_ytop, g_ybase or None, g_mu, g_std)."""

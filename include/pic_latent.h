@@ -220,6 +220,22 @@ int pic_slice_forward(const float *y_top, const float *y_base, const float *mu, 
                       pic_stream_t stream);
 
 /*
+ * (3a) Multi-quality form of (3): the quality sweep of ONE set of latents (train.py check_levels_np sweeps,
+ * test/functions_encode.py:153-196 per-level loops; BASELINE config "quality sweep q = 0..1 in 100 steps").  For each
+ * of `units` input units and each of `levels` qualities q01_levels[u][l] (device, level-minor): threshold, mask,
+ * y_hat, likelihood, index, symbols and rate of output unit u * levels + l.  Inputs are [units][n]; every output is
+ * [units][levels][n] (thr_out / rate [units][levels]); thr_out is required (it carries the thresholds from the select
+ * launch to the apply launch).  The `levels` outputs of a unit read the SAME input block: inputs cross HBM once
+ * (the rest are L2 hits), so the sweep is bound by its 16 B/element of output.  Evaluation mode (no noise).
+ * n_per_unit <= pic_fused_max_elems().
+ */
+int pic_slice_forward_multi(const float *y_top, const float *y_base, const float *mu, const float *std,
+                            const float *q01_levels, int levels, const float *scale_table, int table_len,
+                            float scale_bound, float lik_bound, int64_t n_per_unit, int64_t units, float *mask,
+                            float *y_hat, float *lik, int32_t *idx, int32_t *symbols, float *thr_out, double *rate,
+                            pic_stream_t stream);
+
+/*
  * (4) Backward of (3) (autograd of the same lines).  `mask` is the forward
  * mask; g_lik / g_yhat nullable (treated as zero); g_ybase nullable.  noise NULL => eval
  * forward (round() blocks the gradient into y_m).
@@ -273,6 +289,18 @@ int pic_slice_forward_host(const float *y_top, const float *y_base, const float 
                            int64_t chunk_units, float *mask, float *y_hat, float *lik,
                            int32_t *idx, int32_t *symbols, float *thr_out, double *rate,
                            void *device_buf, size_t device_buf_bytes);
+
+/*
+ * (6a) Compact-output form of (6) for the codec (eval) forward: the mask is {0,1} and the scale index lies in
+ * [0, table_len) with table_len <= 256 (64 in the reference, models/pic.py:12-18), so both return as ONE BYTE per
+ * element -- 10 instead of 16 bytes per element cross PCIe on the way back.  y_hat / lik (nullable) stay f32.
+ * Same pipeline, same scratch size as (6).
+ */
+int pic_slice_forward_host_compact(const float *y_top, const float *y_base, const float *mu, const float *std, float q01,
+                                   const float *q01_per_unit_host, const float *scale_table_host, int table_len,
+                                   float scale_bound, float lik_bound, int64_t n_per_unit, int64_t units,
+                                   int64_t chunk_units, uint8_t *mask_u8, float *y_hat, float *lik, uint8_t *idx_u8,
+                                   void *device_buf, size_t device_buf_bytes);
 
 #ifdef __cplusplus
 }

@@ -407,6 +407,18 @@ def test_host_pipeline(pic, dev):
     assert np.array_equal(thr.numpy(), ref["thr"])
     assert_lik_close(outs["lik"].numpy(), ref["lik"])
     assert np.allclose(rate.numpy(), ref["rate"], rtol=1e-5, atol=1e-6)
+    # compact outputs (C ABI 6a): one byte per mask / index element, f32 y_hat and likelihood unchanged
+    m8 = torch.zeros(units, n, dtype=torch.uint8).pin_memory()
+    i8 = torch.zeros(units, n, dtype=torch.uint8).pin_memory()
+    yh = torch.empty(units, n, dtype=torch.float32).pin_memory()
+    lk = torch.empty(units, n, dtype=torch.float32).pin_memory()
+    rc = L.pic_slice_forward_host_compact(y_top.data_ptr(), y_base.data_ptr(), mu.data_ptr(), std.data_ptr(), 0.5,
+                                          q_host.data_ptr(), tb.data_ptr(), 64, 0.11, 1e-9, n, units, chunk,
+                                          m8.data_ptr(), yh.data_ptr(), lk.data_ptr(), i8.data_ptr(), buf.data_ptr(), nbytes)
+    assert rc == 0, rc
+    assert np.array_equal(m8.numpy().astype(np.float32), ref["mask"])
+    assert np.array_equal(i8.numpy().astype(np.int32), ref["idx"])
+    assert np.array_equal(yh.numpy(), outs["y_hat"].numpy()) and np.array_equal(lk.numpy(), outs["lik"].numpy())
 
 
 def test_tiled_select_single_process(pic, dev):
@@ -851,3 +863,21 @@ def test_rank_order_export(pic, dev):
             assert np.array_equal(support, mask[u]), (pr, u)
             thr = np.quantile(std[u].astype(np.float64), 1.0 - pr * 0.1)   # only to count the ties
             assert kept >= int(np.ceil(pr * 0.1 * n)) - 1
+
+
+def test_slice_forward_multi_quality_sweep(pic, dev):
+    """pic_slice_forward_multi == one pic_slice_forward per quality on the same latents (bit-exact, all outputs)."""
+    rng = np.random.default_rng(31)
+    units, n = 3, 32 * 32 * 48
+    y_top, y_base, mu, std = (T(a, dev) for a in trained_like(rng, (units, n)))
+    table = T(scale_table(), dev)
+    prs = [0, 0.3, 1.0, 2.5, 5.0, 9.9, 10]
+    want = ("mask", "y_hat", "lik", "idx", "symbols", "rate")
+    multi = pic.ops.slice_forward_multi(y_top, y_base, mu, std, units, prs, table, want=want)
+    for l, pr in enumerate(prs):
+        one = pic.ops.slice_forward(y_top, y_base, mu, std, units, pic.ops.pr_to_q01(pr), table,
+                                    want=want + ("thr",))
+        for k in ("mask", "y_hat", "lik", "idx", "symbols"):
+            assert torch.equal(multi[k][:, l], one[k]), (k, pr)
+        assert torch.equal(multi["thr"][:, l], one["thr"]), pr
+        np.testing.assert_allclose(N(multi["rate"][:, l]), N(one["rate"]), rtol=1e-6)   # f32 partial sums, other order
