@@ -918,7 +918,7 @@ struct LeanSmem {
 };
 constexpr int kLsBelow = 40, kLsNan = 41, kLsOvf = 42, kLsPoolNext = 43, kLsMaxK = 44, kLsPivLo = 45, kLsPivHi = 46;
 
-template <int CT, int MINB>
+template <int CT, int MINB, int VPI = 4, bool DB = false>
 __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams p, const LeanConfig cfg) {
     extern __shared__ __align__(128) unsigned char dyn[];
     using L = LeanSmem<CT>;
@@ -1105,14 +1105,38 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                 }
                 if (addr > lim) switch_block();
             };
-            constexpr int VPI = 4;
             int j = tid;
-            for (; j + (VPI - 1) * CT < nvec; j += VPI * CT) {
-                float4 v[VPI];
+            if (DB) {
+                // software pipeline: the loads of batch k+1 are issued before batch k is classified, so every thread
+                // has VPI 128-bit loads in flight at all times (the sweep is bound by load latency, not by issue)
+                float4 cur[VPI], nxt[VPI];
+                bool have = j + (VPI - 1) * CT < nvec;
+                if (have) {
 #pragma unroll
-                for (int i = 0; i < VPI; ++i) v[i] = ld_hint(s4 + j + i * CT, pol_last);
+                    for (int i = 0; i < VPI; ++i) cur[i] = ld_hint(s4 + j + i * CT, pol_last);
+                }
+                while (have) {
+                    const int jn = j + VPI * CT;
+                    const bool have_next = jn + (VPI - 1) * CT < nvec;
+                    if (have_next) {
 #pragma unroll
-                for (int i = 0; i < VPI; ++i) classify4(v[i]);
+                        for (int i = 0; i < VPI; ++i) nxt[i] = ld_hint(s4 + jn + i * CT, pol_last);
+                    }
+#pragma unroll
+                    for (int i = 0; i < VPI; ++i) classify4(cur[i]);
+#pragma unroll
+                    for (int i = 0; i < VPI; ++i) cur[i] = nxt[i];
+                    j = jn;
+                    have = have_next;
+                }
+            } else {
+                for (; j + (VPI - 1) * CT < nvec; j += VPI * CT) {
+                    float4 v[VPI];
+#pragma unroll
+                    for (int i = 0; i < VPI; ++i) v[i] = ld_hint(s4 + j + i * CT, pol_last);
+#pragma unroll
+                    for (int i = 0; i < VPI; ++i) classify4(v[i]);
+                }
             }
             for (; j < nvec; j += CT) classify4(ld_hint(s4 + j, pol_last));
             if (CLOSED) {
@@ -1439,10 +1463,73 @@ bool select_lean_usable(const SliceParams &p) {
            aligned16(p.std) && p.units > 0;
 }
 
-template <int CT, int MINB>
+template <int CT, int MINB, int VPI = 4, bool DB = false>
 static int launch_lean_t(const SliceParams &p, cudaStream_t stream) {
     using L = LeanSmem<CT>;
-    auto kern = select_lean_kernel<CT, MINB>;
+    auto kern = select_lean_kernel<CT, MINB, VPI, DB>;
+    int dev = 0;
+    PIC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return PIC_ERR_INVALID_ARGUMENT;
+    static bool configured[64] = {false};
+    static int occ_cache[64] = {0};
+    static size_t occ_smem[64] = {0};
+    if (!configured[dev]) {
+        PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_optin()));
+        configured[dev] = true;
+    }
+    static const int pool_env = env_int("PIC_LEAN_POOL", 0);
+    LeanConfig cfg;
+    cfg.one = 1u;
+    cfg.k0 = private_entries(p.n, CT);
+    cfg.pool_blocks = pool_env > 0 ? pool_env : 64;
+    const size_t smem = L::total(cfg);
+    if (smem > static_cast<size_t>(tma_smem_optin())) return PIC_ERR_TOO_LARGE;
+    if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
+        int occ = 1;
+        PIC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CT, smem));
+        occ_cache[dev] = occ < 1 ? 1 : occ;
+        occ_smem[dev] = smem;
+    }
+    const int64_t max_grid = static_cast<int64_t>(sm_count()) * occ_cache[dev];
+    const int grid = static_cast<int>(p.units < max_grid ? p.units : max_grid);
+    kern<<<grid, CT, smem, stream>>>(p, cfg);
+    return launch_status();
+}
+
+int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
+    // measured on B200 (scripts/select_tune.py; 1010 Kodak units): 256 threads x 4 CTAs/SM x 4 loads in flight 59.6 us,
+    // 256 x 3 x 8 loads 56.8 us (the sweep is bound by load latency: bytes in flight beat occupancy), 5 or 6 CTAs/SM
+    // (register-capped) 73-82 us, a register double-buffered load pipeline 65 us.  Smaller units prefer the 4-CTA form
+    // (32768: 42.8 vs 45.7 us; 8192: 43.7 vs 49.1 us).  At most one unit per SM: 512-thread CTAs (101 units: 15.0 vs 17.0 us).
+    static const int ct = env_int("PIC_LEAN_CT", 0);
+    static const int vpi = env_int("PIC_LEAN_VPI", 0);
+    const bool few = p.units <= sm_count();
+    const int use = ct ? ct : (few ? 512 : 256);
+    if (use == 512) return launch_lean_t<512, 2, 4>(p, stream);
+    const int v = vpi ? vpi : (p.n >= 40000 ? 8 : 4);
+    if (v == 8) return launch_lean_t<256, 3, 8>(p, stream);
+    return launch_lean_t<256, 4, 4>(p, stream);
+}
+
+#ifdef PIC_PHASE_TIMING
+extern "C" int pic_debug_tma_phase_clocks(long long *out, int reset) {
+    cudaDeviceSynchronize();
+    long long z[16] = {0};
+    if (reset) return cudaMemcpyToSymbol(g_tma_phase_clk, z, sizeof(z)) == cudaSuccess ? 0 : -4;
+    return cudaMemcpyFromSymbol(out, g_tma_phase_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -4;
+}
+#endif
+
+bool select_lean_usable(const SliceParams &p) {
+    static const int enabled = env_int("PIC_LEAN_SELECT", 1);
+    return enabled && p.apply_kind == 0 && !p.thr_in && p.n % 4 == 0 && p.n > kCandMax && p.n <= kFusedMaxElems &&
+           aligned16(p.std) && p.units > 0;
+}
+
+template <int CT, int MINB, int VPI = 4, bool DB = false>
+static int launch_lean_t(const SliceParams &p, cudaStream_t stream) {
+    using L = LeanSmem<CT>;
+    auto kern = select_lean_kernel<CT, MINB, VPI, DB>;
     int dev = 0;
     PIC_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return PIC_ERR_INVALID_ARGUMENT;
@@ -1480,8 +1567,15 @@ int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
     const int use = ct ? ct : (few ? 512 : 256);   // measured: 101 Kodak units 15.0 us (512) vs 17.0 (256, 1024)
     if (use == 1024) return launch_lean_t<1024, 1>(p, stream);
     if (use == 512) return launch_lean_t<512, 2>(p, stream);
-    if (minb == 5) return launch_lean_t<256, 5>(p, stream);
-    if (minb == 6) return launch_lean_t<256, 6>(p, stream);
+    static const int vpi = env_int("PIC_LEAN_VPI", 4);
+    if (minb == 5) return vpi == 2 ? launch_lean_t<256, 5, 2>(p, stream) : launch_lean_t<256, 5>(p, stream);
+    if (minb == 6) return vpi == 2 ? launch_lean_t<256, 6, 2>(p, stream) : launch_lean_t<256, 6>(p, stream);
+    if (vpi == 2) return launch_lean_t<256, 4, 2>(p, stream);
+    if (vpi == 8) return launch_lean_t<256, 3, 8>(p, stream);
+    static const int db = env_int("PIC_LEAN_DB", 0);
+    if (db == 4) return launch_lean_t<256, 3, 4, true>(p, stream);
+    if (db == 8) return launch_lean_t<256, 2, 8, true>(p, stream);
+    if (db == 2) return launch_lean_t<256, 4, 2, true>(p, stream);
     return launch_lean_t<256, 4>(p, stream);
 }
 

@@ -1,0 +1,89 @@
+"""Worker of tests/test_gpu_multi.py: launched with torch.distributed.run, one rank per GPU (NCCL).
+Every rank holds a RAGGED band of each unit; the thresholds of the whole units come from the tiled select --
+once with the collectives issued inside libpic_latent.so (pic_tiled_select_threshold), once carried by
+torch.distributed -- and must equal the oracle's quantile of the full unit bit for bit on every rank; the local
+masks / outputs must equal the oracle's slice restricted to the band."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+ROOT = os.path.dirname(TESTS)
+for p in (ROOT, TESTS, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import pic_oracle as po  # noqa: E402  (test infrastructure: the checker)
+from _common import LIK_ATOL, LIK_RTOL, scale_table, trained_like  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import pic_b200
+    from pic_b200 import distributed as pdist
+    from pic_b200 import ops
+
+    po.build()
+    units, n = 7, 3 * 40000 + 7                     # not divisible by the rank count, not a multiple of 4
+    rng = np.random.default_rng(2024)                # same data on every rank
+    y_top, y_base, mu, std = trained_like(rng, (units, n))
+    std[:, ::3] = np.round(std[:, ::3] * 8) / 8      # ties across the band boundaries
+    std[1, :] = 0.5                                   # all-equal unit
+    std[2, 11] = np.nan                               # NaN unit -> NaN threshold, all-false mask
+    prs = [0.5, 5, 9.9999, 0, 10, 1e-4, 7.3]
+    # ragged bands: rank r gets a share proportional to r + 1
+    cuts = np.concatenate([[0], np.cumsum([(r + 1) for r in range(world)])]) * n // (world * (world + 1) // 2)
+    cuts[-1] = n
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    band = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, lo:hi])).to(dev)  # noqa: E731
+    q = ops.q01_tensor(prs, dev)
+    comm = pdist.NcclTileComm(dev)
+    std_l = band(std)
+    thr_lib = pdist.tiled_select_threshold(std_l, units, n, q, comm=comm)
+    thr_td = pdist.tiled_select_threshold(std_l, units, n, q)
+    table = scale_table()
+    ref = po.slice_forward(y_top, y_base, mu, std, prs, table)
+    ok = True
+    msgs = []
+
+    def check(cond, what):
+        nonlocal ok
+        if not cond:
+            ok = False
+            msgs.append(what)
+
+    check(np.array_equal(thr_lib.cpu().numpy(), ref["thr"], equal_nan=True), "library-issued NCCL thresholds != oracle")
+    check(np.array_equal(thr_td.cpu().numpy(), ref["thr"], equal_nan=True), "torch.distributed thresholds != oracle")
+    every = [torch.zeros_like(thr_lib) for _ in range(world)]
+    dist.all_gather(every, thr_lib)
+    check(all(np.array_equal(every[0].cpu().numpy(), e.cpu().numpy(), equal_nan=True) for e in every), "ranks disagree")
+    out = pdist.tiled_slice_forward(band(y_top), band(y_base), band(mu), std_l, units, n, q, torch.from_numpy(table).to(dev),
+                                    want=("mask", "y_hat", "lik", "idx"), comm=comm)
+    torch.cuda.synchronize()
+    for k in ("mask", "y_hat", "idx"):
+        check(np.array_equal(out[k].cpu().numpy(), ref[k][:, lo:hi]), f"{k} of the band != oracle")
+    lik, want = out["lik"].cpu().numpy().astype(np.float64), ref["lik"][:, lo:hi].astype(np.float64)
+    both_nan = np.isnan(lik) & np.isnan(want)       # the NaN scale of unit 2 gives a NaN likelihood on both sides
+    close = np.abs(lik - want) <= LIK_RTOL * np.abs(want) + LIK_ATOL
+    check(bool(np.all(close | both_nan)), "likelihood of the band out of tolerance")
+    comm.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not ok:
+        print(f"[rank {rank}] FAILED: " + "; ".join(msgs), flush=True)
+    dist.destroy_process_group()
+    if rank == 0 and int(flag.item()) == 1:
+        print("TILED_TWO_RANK_OK", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
