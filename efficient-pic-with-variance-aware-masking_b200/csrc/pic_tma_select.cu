@@ -1511,74 +1511,6 @@ int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
     return launch_lean_t<256, 4, 4>(p, stream);
 }
 
-#ifdef PIC_PHASE_TIMING
-extern "C" int pic_debug_tma_phase_clocks(long long *out, int reset) {
-    cudaDeviceSynchronize();
-    long long z[16] = {0};
-    if (reset) return cudaMemcpyToSymbol(g_tma_phase_clk, z, sizeof(z)) == cudaSuccess ? 0 : -4;
-    return cudaMemcpyFromSymbol(out, g_tma_phase_clk, sizeof(long long) * 16) == cudaSuccess ? 0 : -4;
-}
-#endif
-
-bool select_lean_usable(const SliceParams &p) {
-    static const int enabled = env_int("PIC_LEAN_SELECT", 1);
-    return enabled && p.apply_kind == 0 && !p.thr_in && p.n % 4 == 0 && p.n > kCandMax && p.n <= kFusedMaxElems &&
-           aligned16(p.std) && p.units > 0;
-}
-
-template <int CT, int MINB, int VPI = 4, bool DB = false>
-static int launch_lean_t(const SliceParams &p, cudaStream_t stream) {
-    using L = LeanSmem<CT>;
-    auto kern = select_lean_kernel<CT, MINB, VPI, DB>;
-    int dev = 0;
-    PIC_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return PIC_ERR_INVALID_ARGUMENT;
-    static bool configured[64] = {false};
-    static int occ_cache[64] = {0};
-    static size_t occ_smem[64] = {0};
-    if (!configured[dev]) {
-        PIC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_optin()));
-        configured[dev] = true;
-    }
-    static const int pool_env = env_int("PIC_LEAN_POOL", 0);
-    LeanConfig cfg;
-    cfg.one = 1u;
-    cfg.k0 = private_entries(p.n, CT);
-    cfg.pool_blocks = pool_env > 0 ? pool_env : 64;
-    const size_t smem = L::total(cfg);
-    if (smem > static_cast<size_t>(tma_smem_optin())) return PIC_ERR_TOO_LARGE;
-    if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
-        int occ = 1;
-        PIC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CT, smem));
-        occ_cache[dev] = occ < 1 ? 1 : occ;
-        occ_smem[dev] = smem;
-    }
-    const int64_t max_grid = static_cast<int64_t>(sm_count()) * occ_cache[dev];
-    const int grid = static_cast<int>(p.units < max_grid ? p.units : max_grid);
-    kern<<<grid, CT, smem, stream>>>(p, cfg);
-    return launch_status();
-}
-
-int launch_select_lean(const SliceParams &p, cudaStream_t stream) {
-    static const int ct = env_int("PIC_LEAN_CT", 0);
-    static const int minb = env_int("PIC_LEAN_MINB", 4);
-    // at most one unit per SM (per-slice launches, single images): wider CTAs finish each unit sooner
-    const bool few = p.units <= sm_count();
-    const int use = ct ? ct : (few ? 512 : 256);   // measured: 101 Kodak units 15.0 us (512) vs 17.0 (256, 1024)
-    if (use == 1024) return launch_lean_t<1024, 1>(p, stream);
-    if (use == 512) return launch_lean_t<512, 2>(p, stream);
-    static const int vpi = env_int("PIC_LEAN_VPI", 4);
-    if (minb == 5) return vpi == 2 ? launch_lean_t<256, 5, 2>(p, stream) : launch_lean_t<256, 5>(p, stream);
-    if (minb == 6) return vpi == 2 ? launch_lean_t<256, 6, 2>(p, stream) : launch_lean_t<256, 6>(p, stream);
-    if (vpi == 2) return launch_lean_t<256, 4, 2>(p, stream);
-    if (vpi == 8) return launch_lean_t<256, 3, 8>(p, stream);
-    static const int db = env_int("PIC_LEAN_DB", 0);
-    if (db == 4) return launch_lean_t<256, 3, 4, true>(p, stream);
-    if (db == 8) return launch_lean_t<256, 2, 8, true>(p, stream);
-    if (db == 2) return launch_lean_t<256, 4, 2, true>(p, stream);
-    return launch_lean_t<256, 4>(p, stream);
-}
-
 void select_tma_counters(unsigned long long *sampled, unsigned long long *fallback) {
     unsigned long long s = 0, f = 0;
     cudaMemcpyFromSymbol(&s, g_tma_sampled_units, sizeof(s));
