@@ -4,7 +4,7 @@ functions (through oracle/ref_shim.py) on seeded inputs, in the build container.
     python oracle/gen_golden.py            # rewrites tests/golden/
 
 The committed fixtures are what pins the C oracle (tests/test_oracle_golden.py) and, on the
-GPU box (where /root/reference does not exist), the CUDA path (tests/test_golden_gpu.py).
+GPU box (where /root/reference does not exist), the CUDA path (tests/test_gpu_parity.py).
 Torch used for generation is recorded in tests/golden/MANIFEST.json.
 """
 from __future__ import annotations

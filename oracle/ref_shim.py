@@ -2,7 +2,7 @@
 
 Used only in the build container (where /root/reference exists) by
 ``oracle/gen_golden.py`` to generate the golden vectors committed under
-``tests/golden/`` and by ``oracle/check_oracle_vs_reference.py`` to pin the C
+``tests/golden/`` and by ``oracle/gen_golden_model*.py`` / ``gen_golden_codec.py`` (model- and coder-derived vectors); ``tests/test_oracle_golden.py`` pins the C
 restatement.  Nothing on the product path, in ``-m gpu`` tests, ``smoke()`` or
 ``bench.py`` imports this file: /root/reference does not exist on the GPU box.
 

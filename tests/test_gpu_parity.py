@@ -881,3 +881,43 @@ def test_slice_forward_multi_quality_sweep(pic, dev):
             assert torch.equal(multi[k][:, l], one[k]), (k, pr)
         assert torch.equal(multi["thr"][:, l], one["thr"]), pr
         np.testing.assert_allclose(N(multi["rate"][:, l]), N(one["rate"]), rtol=1e-6)   # f32 partial sums, other order
+
+
+# ------------------------------------------------------------------------------------------ REM model (config[3])
+@pytest.mark.parametrize("q_name", ["pr2.5", "pr5"])
+def test_rem_model_derived(pic, dev, q_name):
+    """BASELINE config[3]: every call the random-init reference REM model (mu_std, dimension middle, check_levels
+    [0.75]) made into the path -- masking at the checkpoint / bar / star / block qualities, the duplicated attention
+    mask handed to the REM, gaussian_conditional and build_indexes -- reproduced by the CUDA drop-ins."""
+    G = golden("model_rem.npz")
+    masking = pic.ChannelMask("point-based-std")
+    n_mask = int(G[f"{q_name}/n_mask"])
+    assert n_mask == 40
+    recs = []
+    for i in range(n_mask):
+        scale, pr = G[f"{q_name}/mask{i}/scale"], float(G[f"{q_name}/mask{i}/pr"])
+        want = unpack_mask(G[f"{q_name}/mask{i}/mask"], scale.shape)
+        got = masking(T(scale, dev), pr=pr, mask_pol="point-based-std")
+        assert got.dtype == torch.float32 and np.array_equal(N(got), want), (i, pr)
+        recs.append((scale, pr, want))
+    n_att = int(G[f"{q_name}/n_att"])
+    assert n_att == 10
+    for i in range(n_att):
+        scale, pr, _ = recs[int(G[f"{q_name}/att{i}/src"])]
+        shape = tuple(G[f"{q_name}/att{i}/shape"])
+        want = unpack_mask(G[f"{q_name}/att{i}/mask"], shape)
+        got = masking.attention_mask(T(scale, dev), pr, training=False, mu_std=True)
+        assert tuple(got.shape) == shape == (1, 64, 16, 16) and np.array_equal(N(got), want), i
+    if q_name == "pr2.5":
+        gc = pic.GaussianConditional(None)
+        gc.scale_table = pic.get_scale_table()
+        gc = gc.to(dev)
+        for i in range(int(G["pr2.5/n_gc"])):
+            inp, sc = T(G[f"pr2.5/gc{i}/inputs"], dev), T(G[f"pr2.5/gc{i}/scales"], dev)
+            means = T(G[f"pr2.5/gc{i}/means"], dev) if f"pr2.5/gc{i}/means" in G.files else None
+            out, lik = gc(inp, sc, means, training=False)
+            assert np.array_equal(N(out), G[f"pr2.5/gc{i}/outputs"]), i
+            assert_lik_close(N(lik), G[f"pr2.5/gc{i}/lik"], f"rem gc{i}")
+            assert np.array_equal(N(gc.build_indexes(sc)), G[f"pr2.5/gc{i}/idx"]), i
+        for i in range(int(G["pr2.5/n_idx"])):
+            assert np.array_equal(N(gc.build_indexes(T(G[f"pr2.5/idx{i}/scales"], dev))), G[f"pr2.5/idx{i}/idx"]), i

@@ -155,3 +155,46 @@ def test_model_derived_config1(q_name, pr):
         assert np.array_equal(o["mask"], unpack_mask(G[f"{q_name}/slice{k}/mask"], (1, std.size))), (q_name, k)
         assert np.array_equal(o["y_hat"], f(G[f"{q_name}/slice{k}/y_hat"])), (q_name, k)
         assert_lik_close(o["lik"], f(G[f"{q_name}/slice{k}/lik"]), f"{q_name}/slice{k}")
+
+
+# ------------------------------------------------------------------------------------------ REM model (config[3])
+def _rem_records(G, q_name):
+    masks = [(G[f"{q_name}/mask{i}/scale"], float(G[f"{q_name}/mask{i}/pr"]), G[f"{q_name}/mask{i}/mask"])
+             for i in range(int(G[f"{q_name}/n_mask"]))]
+    return masks
+
+
+@pytest.mark.parametrize("q_name", ["pr2.5", "pr5"])
+def test_rem_model_masking_calls(q_name):
+    """Every masking() call the random-init reference REM model made (checkpoint pass at q = 0.75, bar / star masks of
+    apply_latent_enhancement, block mask on the REM-refined scale; models/rem_pic.py:182-189, 382-391, 583-586):
+    the oracle reproduces each mask bit for bit."""
+    G = golden("model_rem.npz")
+    masks = _rem_records(G, q_name)
+    assert len(masks) == 40 and int(G[f"{q_name}/n_mask_checkpoint"]) == 10
+    prs = set()
+    for scale, pr, packed in masks:
+        flat = scale.reshape(scale.shape[0], -1)
+        got, _ = po.channel_mask(flat, pr)
+        assert np.array_equal(got, unpack_mask(packed, flat.shape)), pr
+        prs.add(round(pr, 6))
+    assert 0.75 in prs and float(G[f"{q_name}/pr"]) in prs      # checkpoint / bar quality and the requested one
+
+
+def test_rem_model_entropy_calls():
+    """gaussian_conditional(...) and build_indexes(...) as the REM model called them."""
+    G = golden("model_rem.npz")
+    table = scale_table()
+    n_gc = int(G["pr2.5/n_gc"])
+    assert n_gc == 20
+    for i in range(n_gc):
+        inp, sc = G[f"pr2.5/gc{i}/inputs"], G[f"pr2.5/gc{i}/scales"]
+        means = G[f"pr2.5/gc{i}/means"] if f"pr2.5/gc{i}/means" in G.files else None
+        f = lambda a: None if a is None else a.reshape(1, -1)  # noqa: E731
+        out, lik = po.gaussian_forward(f(inp), f(sc), f(means))
+        assert np.array_equal(out, f(G[f"pr2.5/gc{i}/outputs"])), i
+        assert_lik_close(lik, f(G[f"pr2.5/gc{i}/lik"]), f"rem gc{i}")
+        assert np.array_equal(po.build_indexes(f(sc), table), f(G[f"pr2.5/gc{i}/idx"])), i
+    for i in range(int(G["pr2.5/n_idx"])):
+        sc = G[f"pr2.5/idx{i}/scales"].reshape(1, -1)
+        assert np.array_equal(po.build_indexes(sc, table), G[f"pr2.5/idx{i}/idx"].reshape(1, -1)), i
