@@ -2,7 +2,7 @@
 
 Public surface = the reference's own API for this path (drop-in):
     ChannelMask, ste_round                      (layers/channel_mask.py)
-    EntropyModel, GaussianConditional           (entropy_models/entropy_models.py)
+    EntropyModel, GaussianConditional, EntropyBottleneck   (entropy_models/entropy_models.py)
     get_scale_table                             (models/pic.py:12-17)
 plus the fused per-slice operator ``progressive_slice_forward`` and the spatially tiled
 multi-GPU select (``distributed``), and the host-side coder after the path (``codec``: CDF tables,
@@ -17,7 +17,7 @@ import torch
 from . import _lib, codec, distributed, ops
 from ._lib import LIB_PATH, build, lib
 from .channel_mask import ChannelMask, ste_round
-from .entropy_models import EntropyModel, GaussianConditional, LowerBound
+from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound
 from .functional import lrp_merge, progressive_slice_forward, rate_bpp, rem_merge
 
 SCALES_MIN = 0.11
@@ -30,5 +30,5 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
-__all__ = ["ChannelMask", "ste_round", "EntropyModel", "GaussianConditional", "LowerBound",
+__all__ = ["ChannelMask", "ste_round", "EntropyModel", "EntropyBottleneck", "GaussianConditional", "LowerBound",
            "progressive_slice_forward", "rate_bpp", "lrp_merge", "rem_merge", "get_scale_table", "ops", "codec", "distributed", "build", "lib", "LIB_PATH"]

@@ -14,7 +14,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("PIC_LIB_PATH") or os.path.join(_PKG, "libpic_latent.so")   # override: kernel experiments
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_tma_select.cu", "pic_rank.cu", "pic_host.cu", "pic_rans.cpp")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pic_latent.cu", "pic_tma_select.cu", "pic_rank.cu", "pic_bottleneck.cu", "pic_host.cu", "pic_rans.cpp")]
 _HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("pic_math.cuh", "pic_fast.cuh", "pic_select.cuh", "pic_gselect.cuh", "pic_params.h")] + [
     os.path.join(_ROOT, "include", "pic_latent.h"), os.path.join(_ROOT, "include", "pic_codec.h")]
 
@@ -79,6 +79,10 @@ SIGNATURES = {
     "pic_quantize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pic_dequantize": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pic_log_sum": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "pic_bottleneck_params_per_channel": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "pic_bottleneck_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _f32, _vp, _vp, _vp]),
+    "pic_bottleneck_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _f32,
+                                          _vp, _vp, _vp, _vp, _vp, _vp]),
     # include/pic_codec.h (host code: CDF tables + rANS)
     "pic_pmf_to_quantized_cdf": (C.c_int, [_vp, _i32, _i32, _vp]),
     "pic_rans_stream_bound": (_i64, [_i64]),

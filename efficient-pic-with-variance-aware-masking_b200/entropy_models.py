@@ -286,6 +286,182 @@ class _GaussianForward(torch.autograd.Function):
         return g_in, g_sc, g_mu, None, None, None, None
 
 
+class _BottleneckFn(torch.autograd.Function):
+    """EntropyBottleneck.forward as one kernel, with one backward kernel for z, the medians and every parameter."""
+
+    @staticmethod
+    def forward(ctx, z, noise, medians, lik_bound, filters, *raw):
+        nl = len(filters) + 1
+        mats, biases, factors = raw[:nl], raw[nl:2 * nl], raw[2 * nl:]
+        C = z.shape[1]
+        params = torch.cat([t.reshape(C, -1) for t in (*mats, *biases, *factors)], dim=1).contiguous()
+        outputs, lik = ops.bottleneck_forward(z, medians, params, filters, noise=noise, lik_bound=lik_bound)
+        ctx.save_for_backward(z, noise, medians, params)
+        ctx.cfg = (lik_bound, filters, [t.shape for t in raw])
+        return outputs, lik
+
+    @staticmethod
+    def backward(ctx, g_out, g_lik):
+        z, noise, medians, params = ctx.saved_tensors
+        lik_bound, filters, shapes = ctx.cfg
+        g_out = None if g_out is None else g_out.contiguous()
+        g_lik = torch.zeros_like(z) if g_lik is None else g_lik.contiguous()
+        g_z, g_params, g_med = ops.bottleneck_backward(z, medians, params, filters, g_lik, g_out, noise, lik_bound)
+        grads, o = [], 0
+        for shp in shapes:
+            cnt = shp[1] * shp[2]
+            grads.append(g_params[:, o:o + cnt].reshape(shp))
+            o += cnt
+        return (g_z, None, g_med, None, None, *grads)
+
+
+class EntropyBottleneck(EntropyModel):
+    """Drop-in for the reference's EntropyBottleneck (entropy_models/entropy_models.py:296-528): same constructor,
+    parameter names (_matrix{i}, _bias{i}, _factor{i}, quantiles, target) and methods.  forward() runs as one kernel
+    on z where the conv wrote it (no permute), its backward as one kernel that also accumulates the parameter
+    gradients; update() / compress() / decompress() keep the reference's logic over the package's coder."""
+
+    _offset: Tensor
+
+    def __init__(self, channels: int, *args: Any, tail_mass: float = 1e-9, init_scale: float = 10,
+                 filters: Tuple[int, ...] = (3, 3, 3, 3), **kwargs: Any):
+        super().__init__(*args, **kwargs)
+        import numpy as np
+
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        if len(self.filters) != 4 or any(f < 1 or f > 4 for f in self.filters):
+            raise ValueError("the kernel supports the reference's four hidden layers of up to 4 units")
+        filters = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / filters[i + 1]))
+            matrix = torch.Tensor(self.channels, filters[i + 1], filters[i])
+            matrix.data.fill_(init)
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(matrix))
+            bias = torch.Tensor(self.channels, filters[i + 1], 1)
+            nn.init.uniform_(bias, -0.5, 0.5)
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(bias))
+            if i < len(self.filters):
+                factor = torch.Tensor(self.channels, filters[i + 1], 1)
+                nn.init.zeros_(factor)
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(factor))
+        self.quantiles = nn.Parameter(torch.Tensor(self.channels, 1, 3))
+        init = torch.Tensor([-self.init_scale, 0, self.init_scale])
+        self.quantiles.data = init.repeat(self.quantiles.size(0), 1, 1)
+        target = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+
+    def _get_medians(self) -> Tensor:
+        return self.quantiles[:, :, 1:2]
+
+    def _raw_parameters(self):
+        nl = len(self.filters) + 1
+        return ([getattr(self, f"_matrix{i:d}") for i in range(nl)] + [getattr(self, f"_bias{i:d}") for i in range(nl)] +
+                [getattr(self, f"_factor{i:d}") for i in range(nl - 1)])
+
+    def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
+        """Reference 403-420 (plain torch: used by update() and loss() on a handful of values per channel)."""
+        import torch.nn.functional as F
+
+        logits = inputs
+        for i in range(len(self.filters) + 1):
+            matrix = getattr(self, f"_matrix{i:d}")
+            bias = getattr(self, f"_bias{i:d}")
+            if stop_gradient:
+                matrix, bias = matrix.detach(), bias.detach()
+            logits = torch.matmul(F.softplus(matrix), logits) + bias
+            if i < len(self.filters):
+                factor = getattr(self, f"_factor{i:d}")
+                if stop_gradient:
+                    factor = factor.detach()
+                logits = logits + torch.tanh(factor) * torch.tanh(logits)
+        return logits
+
+    def loss(self) -> Tensor:
+        logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
+        return torch.abs(logits - self.target).sum()
+
+    def _likelihood(self, inputs: Tensor) -> Tensor:
+        """Reference 422-434 on values laid out [C, 1, N] (its internal layout): no quantisation, no bound."""
+        C = inputs.shape[0]
+        z = inputs.reshape(C, -1).t().reshape(1, -1, C).permute(0, 2, 1).contiguous()       # [1, C, N]
+        zero = torch.zeros_like(z)
+        _, lik = _BottleneckFn.apply(z, zero, self._get_medians().reshape(-1).contiguous(), 0.0, self.filters,
+                                     *self._raw_parameters())
+        return lik.reshape(C, 1, -1)
+
+    def forward(self, x: Tensor, training: Optional[bool] = None) -> Tuple[Tensor, Tensor]:
+        if training is None:
+            training = self.training
+        x = x.contiguous()
+        noise = None
+        if training:
+            # the reference draws the noise on the permuted [C, 1, B*S] tensor: same call, same stream, same layout
+            C = x.shape[1]
+            perm = torch.empty((C, 1, x.numel() // C), dtype=x.dtype, device=x.device).uniform_(-0.5, 0.5)
+            noise = perm.reshape(C, x.shape[0], -1).permute(1, 0, 2).reshape(x.shape).contiguous()
+        lik_bound = self.likelihood_lower_bound.value() if self.use_likelihood_bound else 0.0
+        return _BottleneckFn.apply(x, noise, self._get_medians().reshape(-1).contiguous(), lik_bound, self.filters,
+                                   *self._raw_parameters())
+
+    def update(self, force: bool = False) -> bool:
+        """Reference 355-396: per-channel pmf on [median - minima, median + maxima] and its 16-bit CDF."""
+        try:
+            from compressai._CXX import pmf_to_quantized_cdf as normalise
+        except ImportError:
+            normalise = codec.pmf_to_quantized_cdf
+        medians = self.quantiles[:, 0, 1]
+        minima = torch.clamp(torch.ceil(medians - self.quantiles[:, 0, 0]).int(), min=0)
+        maxima = torch.clamp(torch.ceil(self.quantiles[:, 0, 2] - medians).int(), min=0)
+        self._offset = -minima
+        pmf_start = medians - minima
+        pmf_length = maxima + minima + 1
+        max_length = int(pmf_length.max().item())
+        samples = torch.arange(max_length, device=pmf_start.device)[None, :] + pmf_start[:, None, None]
+        lower = self._logits_cumulative(samples - 0.5, stop_gradient=True)
+        upper = self._logits_cumulative(samples + 0.5, stop_gradient=True)
+        sign = -torch.sign(lower + upper)
+        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))[:, 0, :]
+        tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+        cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32, device=pmf.device)
+        for i, p in enumerate(pmf):
+            prob = torch.cat((p[: pmf_length[i]], tail_mass[i]), dim=0)
+            row = normalise(prob.tolist(), self.entropy_coder_precision)
+            cdf[i, : len(row)] = torch.tensor(row, dtype=torch.int32)
+        self._quantized_cdf = cdf
+        self._cdf_length = (pmf_length + 2).int()
+        self._invalidate_tables()
+        return True
+
+    @staticmethod
+    def _build_indexes(size):
+        N, C = size[0], size[1]
+        view = [1] * len(size)
+        view[1] = -1
+        return torch.arange(C).view(*view).int().repeat(N, 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor, n):
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def compress(self, x):
+        indexes = self._build_indexes(x.size()).to(x.device)
+        spatial_dims = len(x.size()) - 2
+        medians = self._extend_ndims(self._get_medians().detach(), spatial_dims)
+        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+        return super().compress(x, indexes, medians, 0)
+
+    def decompress(self, strings, size):
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        indexes = self._build_indexes(output_size).to(self._quantized_cdf.device)
+        medians = self._extend_ndims(self._get_medians().detach(), len(size))
+        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
+        return super().decompress(strings, indexes, medians, 0)
+
+
 class GaussianConditional(EntropyModel):
     """Constructor contract of the reference (entropy_models.py:531-567): `scale_table` is None or a non-empty,
     sorted, positive list / tuple; `scale_bound` > 0 (defaults to 0.11; None takes the table's first entry)."""

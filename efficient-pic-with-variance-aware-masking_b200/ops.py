@@ -441,3 +441,35 @@ def log_sum(x, units: int) -> torch.Tensor:
     out = torch.empty(units, dtype=torch.float64, device=x.device)
     check(lib().pic_log_sum(_ptr(x), n, units, _ptr(out), _stream()), "pic_log_sum")
     return out
+
+
+# ----------------------------------------------------------------------------------- EntropyBottleneck (z)
+@_on_tensor_device
+def bottleneck_forward(z, medians, params, filters, noise=None, lik_bound: float = 1e-9):
+    """EntropyBottleneck.forward on z [B, C, ...]: returns (outputs, likelihood) (pic_bottleneck_forward)."""
+    z, medians, params, noise = (_require(t, nm) for t, nm in ((z, "z"), (medians, "medians"), (params, "params"), (noise, "noise")))
+    B, Cc = z.shape[0], z.shape[1]
+    S = z.numel() // (B * Cc)
+    outputs, lik = torch.empty_like(z), torch.empty_like(z)
+    f = tuple(int(v) for v in filters)
+    check(lib().pic_bottleneck_forward(_ptr(z), _ptr(noise), _ptr(medians), _ptr(params), f[0], f[1], f[2], f[3], B, Cc, S,
+                                       lik_bound, _ptr(outputs), _ptr(lik), _stream()), "pic_bottleneck_forward")
+    return outputs, lik
+
+
+@_on_tensor_device
+def bottleneck_backward(z, medians, params, filters, g_lik, g_out=None, noise=None, lik_bound: float = 1e-9):
+    """Returns (g_z, g_params [C, per_channel], g_medians [C])."""
+    ts = [_require(t, nm) for t, nm in ((z, "z"), (medians, "medians"), (params, "params"), (g_lik, "g_lik"), (g_out, "g_out"),
+                                        (noise, "noise"))]
+    z, medians, params, g_lik, g_out, noise = ts
+    B, Cc = z.shape[0], z.shape[1]
+    S = z.numel() // (B * Cc)
+    g_z = torch.empty_like(z)
+    g_params = torch.empty_like(params)
+    g_med = torch.empty_like(medians)
+    f = tuple(int(v) for v in filters)
+    check(lib().pic_bottleneck_backward(_ptr(z), _ptr(noise), _ptr(medians), _ptr(params), f[0], f[1], f[2], f[3], B, Cc, S,
+                                        lik_bound, _ptr(g_lik), _ptr(g_out), _ptr(g_z), _ptr(g_params), _ptr(g_med), _stream()),
+          "pic_bottleneck_backward")
+    return g_z, g_params, g_med

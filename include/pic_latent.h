@@ -274,6 +274,26 @@ int pic_log_sum(const float *x, int64_t n_per_unit, int64_t units, double *out,
                 pic_stream_t stream);
 
 /*
+ * (5a) EntropyBottleneck for the hyper-latent z -- entropy_models/entropy_models.py:403-436 (_logits_cumulative,
+ * _likelihood) and 449-492 (forward), with their autograd.  z / noise / outputs / lik: [batch, channels, spatial]
+ * (the contiguous NCHW tensor; the reference's permute to [C, 1, B*S] and back is not needed).  noise NULL: eval,
+ * outputs = round(z - median) + median; else outputs = z + noise (the caller draws the noise as the reference does).
+ * medians: [channels] (quantiles[:, 0, 1]).  params: [channels][pic_bottleneck_params_per_channel()] RAW parameters
+ * of the per-channel scalar network with filters (1, f1, f2, f3, f4, 1), packed per channel as all _matrix{i}
+ * (row-major [f_{i+1}][f_i]), then all _bias{i}, then all _factor{i} (i = 0..3); softplus / tanh are applied inside.
+ * lik_bound: likelihood lower bound (0 disables).  Backward: g_params [channels][per_channel] and g_medians (nullable)
+ * are overwritten; g_z (nullable) is the gradient of z (identity through the noise in training, 0 through round()).
+ */
+int pic_bottleneck_params_per_channel(int f1, int f2, int f3, int f4);
+int pic_bottleneck_forward(const float *z, const float *noise, const float *medians, const float *params, int f1, int f2,
+                           int f3, int f4, int64_t batch, int64_t channels, int64_t spatial, float lik_bound,
+                           float *outputs, float *lik, pic_stream_t stream);
+int pic_bottleneck_backward(const float *z, const float *noise, const float *medians, const float *params, int f1, int f2,
+                            int f3, int f4, int64_t batch, int64_t channels, int64_t spatial, float lik_bound,
+                            const float *g_lik, const float *g_out, float *g_z, float *g_params, float *g_medians,
+                            pic_stream_t stream);
+
+/*
  * (6) Host-buffer form of (3) for callers whose latents live in host memory (the reference's
  * CPU path, or an FFI caller without device tensors).  All tensor pointers are HOST memory
  * (pinned memory makes the copies asynchronous); units are streamed through the device in
