@@ -76,7 +76,9 @@ def test_bottleneck_kernels(mode):
     for n, p in eb.named_parameters():
         want = G[f"{mode}/g_{n}"]
         got = np.zeros_like(want) if p.grad is None else p.grad.cpu().numpy()
-        assert_grad_close(got, want, f"g_{n} {mode}")
+        # a parameter gradient is a sum over all positions of the channel (f32 partial sums in another order than
+        # autograd's, with cancellation): relative 1e-4 plus 2e-5 of the largest entry
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * max(float(np.abs(want).max()), 1e-30), err_msg=f"g_{n} {mode}")
     # the oracle on a larger seeded case, incl. the un-quantised _likelihood entry
     rng = np.random.default_rng(5)
     zz = (rng.normal(size=(4, 6, 9, 7)) * 5).astype(np.float32)
