@@ -726,7 +726,10 @@ def bench_tile(cx: Ctx):
         rec["launches_per_step"] = 9
         rec["collectives_per_step"] = comm.collectives_per_select if hasattr(comm, "collectives_per_select") else 4
         rec["collective"] = "ncclAllReduce(uint32 sum) of the per-slice radix histograms + ncclAllReduce(min), issued by libpic_latent.so"
-        graph = False
+        # the collectives belong to the library's own communicator, so the whole step (kernels + NCCL) can be captured
+        # in a CUDA graph; PIC_TILED_GRAPH=0 keeps it eager
+        graph = bool(args.graph) and os.environ.get("PIC_TILED_GRAPH", "1") != "0"
+        rec["cuda_graph"] = graph
     t = timed_steps(cx, step, max(5, args.steps // 2), 3, graph=graph, windows=3)
     rec.update({"value": units * n / (t["ms"] * 1e-3) / 1e9, "ms_per_step": t["ms"], "windows": t["windows"],
                 "ms_per_step_by_rank": [round(v, 5) for v in cx.gather(t["own_ms"])],

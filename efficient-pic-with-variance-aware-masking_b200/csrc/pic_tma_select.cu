@@ -906,6 +906,7 @@ struct LeanConfig {
     int k0;            // private candidate entries per thread (incl. 4 guard entries)
     int pool_blocks;
     uint32_t one;
+    int prefetch_lines;   // 128-byte lines of the CTA's next unit pulled into L2 during the final phase (0 = off)
 };
 template <int CT>
 struct LeanSmem {
@@ -916,7 +917,8 @@ struct LeanSmem {
     static constexpr size_t kScratch = 256 * 4;
     __host__ __device__ static size_t total(const LeanConfig &c) { return priv(c) + pool(c) + pool_cnt(c) + kHist + kScratch; }
 };
-constexpr int kLsBelow = 40, kLsNan = 41, kLsOvf = 42, kLsPoolNext = 43, kLsMaxK = 44, kLsPivLo = 45, kLsPivHi = 46;
+constexpr int kLsBelow = 130, kLsNan = 131, kLsOvf = 132, kLsPoolNext = 133, kLsMaxK = 134, kLsPivLo = 135, kLsPivHi = 136,
+              kLsSampMin = 137, kLsSampMax = 138;   // scratch words [128, 192) are free in this kernel (no second coarse histogram)
 
 template <int CT, int MINB, int VPI = 4, bool DB = false>
 __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams p, const LeanConfig cfg) {
@@ -1015,6 +1017,12 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
         const float *std_u = p.std + ((p.repeat > 1) ? u / p.repeat : u) * p.n;
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
         const int S = sample_size(n);
+#ifdef PIC_PHASE_TIMING
+        long long lt0 = clock64();
+#define LEAN_STAMP(i) do { if (tid == 0 && blockIdx.x == 0) { const long long t__ = clock64(); g_tma_phase_clk[i] += t__ - lt0; lt0 = t__; } } while (0)
+#else
+#define LEAN_STAMP(i) do {} while (0)
+#endif
         // ---- sample + pivots ---------------------------------------------------------------------------
         float4 samp[KPT4];
         {
@@ -1057,6 +1065,11 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
             const float slack = 0.5f * sqrtf(static_cast<float>(h.count)) + 3.0f;
             const uint32_t k = (warp == 0) ? bucket_interp(h.bin, t - slack, h.count) : bucket_interp(h.bin, t + 1.0f + slack, h.count);
             if (lane == 0) scratch[warp == 0 ? kLsPivLo : kLsPivHi] = k;
+        } else if (warp < 4) {
+            // lowest / highest occupied sample bucket: bounds the digit range of an open-ended bracket (final phase)
+            uint32_t tot;
+            const BinHit h = warp_find2048(hist, warp == 2 ? 0u : static_cast<uint32_t>(S - 1), tot);
+            if (lane == 0) scratch[warp == 2 ? kLsSampMin : kLsSampMax] = h.bin;
         }
         __syncthreads();
         const float plo_f = (klo > 0) ? key_to_float(scratch[kLsPivLo]) : -INFINITY;
@@ -1064,6 +1077,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
         const bool closed = (fabsf(plo_f) < INFINITY) && (fabsf(phi_f) < INFINITY);
         const float mid = 0.5f * plo_f + 0.5f * phi_f;
         const float hw = closed ? fmaxf(__fsub_ru(phi_f, mid), __fsub_ru(mid, plo_f)) : 0.0f;
+        LEAN_STAMP(0);
         // ---- sweep: four 128-bit loads in flight per thread, classification from registers ----------------
         uint32_t addr = slot0, lim = slot0 + static_cast<uint32_t>(cfg.k0 - 4) * kPrivStride, stride = kPrivStride, c0 = 0;
         int cur = -1;
@@ -1164,12 +1178,26 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                 if (wovf) scratch[kLsOvf] = 1u;
             }
         }
+        LEAN_STAMP(1);
+        if (cfg.prefetch_lines > 0) {
+            // The final phase below and the next unit's pivot phase are latency-bound and leave HBM idle: pull the head
+            // of this CTA's NEXT unit into L2 meanwhile, so that its sweep starts on L2 hits
+            int64_t un = u + gridDim.x;
+            while (un < p.units && unit_mode(p.q01_per_unit ? p.q01_per_unit[un] : p.q01) != kModeThreshold) un += gridDim.x;
+            if (un < p.units) {
+                const char *nxt = reinterpret_cast<const char *>(p.std + ((p.repeat > 1) ? un / p.repeat : un) * p.n);
+                const int lines = min(cfg.prefetch_lines, (n * 4 + 127) / 128);
+                for (int l = tid; l < lines; l += CT)
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nxt + static_cast<size_t>(l) * 128));
+            }
+        }
         zero_hist(kHistBins);         // the sample histogram was last read before the sweep
         if (tid == 0) {
             scratch[kScrMinAbove] = 0xffffffffu; scratch[kScrBinMin] = 0xffffffffu; scratch[kScrBinMax] = 0u;
             scratch[kScrListLen] = 0u;
         }
         __syncthreads();
+        LEAN_STAMP(6);
         // ---- final --------------------------------------------------------------------------------------
         const uint32_t c_below = scratch[kLsBelow];
         const uint32_t npool = min(scratch[kLsPoolNext], pool_blocks);
@@ -1209,19 +1237,28 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
             // any NaN -> NaN threshold (torch.quantile)
         } else if (valid) {
             const float dscale = (closed && hw > 1e-30f) ? 1024.0f / hw : 0.0f;
-            const uint32_t obase = float_to_key(plo_f);
-            const uint32_t owidth = float_to_key(phi_f) - obase;
-            const int obits = 32 - __clz(owidth | 1u);
+            // open-ended bracket: the digit spans [okey_lo, okey_hi], the bracket's finite end and the sample's extreme
+            // bucket on the open side (candidates beyond it clamp into the end bin: monotone, and few) -- digits over the
+            // whole float range up to +-inf would crowd the candidates into a handful of bins
+            uint32_t okey_lo = float_to_key(plo_f), okey_hi = float_to_key(phi_f);
+            if (!(fabsf(plo_f) < INFINITY)) okey_lo = max(okey_lo, scratch[kLsSampMin] << 21);
+            if (!(fabsf(phi_f) < INFINITY)) okey_hi = min(okey_hi, ((scratch[kLsSampMax] + 1u) << 21) - 1u);
+            if (okey_hi <= okey_lo) okey_hi = okey_lo + 1u;
+            const int obits = 32 - __clz((okey_hi - okey_lo) | 1u);
             const int oshift = obits > 11 ? obits - 11 : 0;
             auto run_final = [&](auto closed_tag) {
                 constexpr bool CLOSED = decltype(closed_tag)::value;
                 auto tval = [&](float x) { return __fmaf_rn(__fsub_rn(x, mid), dscale, 1024.0f); };
+                auto kdigit = [&](uint32_t k) -> uint32_t {
+                    const uint32_t d = (k - okey_lo) >> oshift;
+                    return k < okey_lo ? 0u : (d > 2047u ? 2047u : d);
+                };
                 auto digit = [&](float x) -> uint32_t {
                     if (CLOSED) {
                         const int di = __float2int_rd(tval(x));
                         return static_cast<uint32_t>(di < 0 ? 0 : (di > 2047 ? 2047 : di));
                     }
-                    return (float_to_key(x) - obase) >> oshift;
+                    return kdigit(float_to_key(x));
                 };
                 const uint32_t dummy_u32 = smem_u32(scratch + kScrDummy + lane);
                 for_my_cands([&](float x, bool ok) {
@@ -1230,6 +1267,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                 });
                 const uint32_t rank = lo - c_below;
                 __syncthreads();
+                LEAN_STAMP(3);
                 if (warp == 0) {
                     uint32_t tot;
                     const BinHit h = warp_find2048(hist, rank, tot);
@@ -1243,6 +1281,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                 valid = hi < c_below + scratch[kScrTmp];
                 if (!valid) return;
                 const bool small = bin_count <= static_cast<uint32_t>(kSmallList);
+                LEAN_STAMP(4);
                 {
                     uint32_t mymin = 0xffffffffu, bmin = 0xffffffffu, bmax = 0u, nhit = 0, hitk = 0;
                     if (CLOSED) {
@@ -1265,7 +1304,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                     } else {
                         for_my_cands([&](float x, bool ok) {
                             const uint32_t k = float_to_key(x);
-                            const uint32_t d = (k - obase) >> oshift;
+                            const uint32_t d = kdigit(k);
                             mymin = (ok & (d > bin)) ? min(mymin, k) : mymin;
                             const bool in = ok & (d == bin);
                             hitk = (in & (nhit == 0u)) ? k : hitk;
@@ -1292,6 +1331,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
                     }
                 }
                 __syncthreads();
+                LEAN_STAMP(5);
                 const uint32_t r_a = rank - bin_below;
                 const uint32_t r_b = r_a + (hi - lo);
                 if (small) {
@@ -1366,6 +1406,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
             if (p.b_out) p.b_out[u] = b_val;
         }
         __syncthreads();   // lists, hist and scratch are reused by the next unit
+        LEAN_STAMP(2);
     }
 }
 
@@ -1482,6 +1523,8 @@ static int launch_lean_t(const SliceParams &p, cudaStream_t stream) {
     cfg.one = 1u;
     cfg.k0 = private_entries(p.n, CT);
     cfg.pool_blocks = pool_env > 0 ? pool_env : 64;
+    static const int pf_env = env_int("PIC_LEAN_PREFETCH", -1);
+    cfg.prefetch_lines = pf_env >= 0 ? pf_env : 0;
     const size_t smem = L::total(cfg);
     if (smem > static_cast<size_t>(tma_smem_optin())) return PIC_ERR_TOO_LARGE;
     if (occ_cache[dev] == 0 || occ_smem[dev] != smem) {
