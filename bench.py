@@ -720,21 +720,34 @@ def bench_tile(cx: Ctx):
         same_ranks = all(bool(torch.equal(every[0], e)) for e in every)
         rec["thresholds_equal"] = {"library_nccl_vs_torch_distributed": same, "across_ranks": same_ranks}
 
+        protocol = os.environ.get("PIC_TILED_PROTOCOL", "sampled")
+        t_s = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm, protocol="sampled")
+        rec["thresholds_equal"]["sampled_vs_rounds"] = bool(torch.equal(t_s, t_c))
+
         def step():
-            thr = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm)
+            thr = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm, protocol=protocol)
             ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, thr_in=thr, want=want, out=outs)
-        rec["launches_per_step"] = 9
-        rec["collectives_per_step"] = comm.collectives_per_select if hasattr(comm, "collectives_per_select") else 4
-        rec["collective"] = "ncclAllReduce(uint32 sum) of the per-slice radix histograms + ncclAllReduce(min), issued by libpic_latent.so"
-        # the collectives belong to the library's own communicator, so the whole step (kernels + NCCL) can be captured
-        # in a CUDA graph; PIC_TILED_GRAPH=0 keeps it eager
-        graph = bool(args.graph) and os.environ.get("PIC_TILED_GRAPH", "1") != "0"
+        rec["protocol"] = protocol
+        if protocol == "sampled":
+            rec["launches_per_step"] = 9     # sample, pool, pivot select, pivots, sweep, pack, merge, cluster select, apply
+            rec["collectives_per_step"] = 2
+            rec["collective"] = ("ncclAllGather of the bands' samples + ncclAllGather of the bracket counts and candidates, issued "
+                                 "by libpic_latent.so (one stream synchronisation per select; histogram rounds only on a miss)")
+            graph = False
+        else:
+            rec["launches_per_step"] = 9
+            rec["collectives_per_step"] = 4
+            rec["collective"] = "ncclAllReduce(uint32 sum) of the per-slice radix histograms + ncclAllReduce(min), issued by libpic_latent.so"
+            # the collectives belong to the library's own communicator, so the whole step (kernels + NCCL) can be captured
+            # in a CUDA graph; PIC_TILED_GRAPH=0 keeps it eager
+            graph = bool(args.graph) and os.environ.get("PIC_TILED_GRAPH", "1") != "0"
         rec["cuda_graph"] = graph
     t = timed_steps(cx, step, max(5, args.steps // 2), 3, graph=graph, windows=3)
     rec.update({"value": units * n / (t["ms"] * 1e-3) / 1e9, "ms_per_step": t["ms"], "windows": t["windows"],
                 "ms_per_step_by_rank": [round(v, 5) for v in cx.gather(t["own_ms"])],
                 "whole_step_frac": (units * n_local * wl["bytes_per_elem"] / (t["own_ms"] * 1e-3) / 1e9) / cx.hbm})
     if comm is not None:
+        rec["sampled_selects_that_fell_back"] = comm.fallbacks
         comm.close()
     del y_top, y_base, mu, std, outs
     torch.cuda.empty_cache()

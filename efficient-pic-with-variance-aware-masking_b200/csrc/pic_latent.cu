@@ -1453,6 +1453,171 @@ static int select_large_or_rounds(const float *std, int64_t n, int64_t units, fl
     return select_rounds(std, n, units, q01, q01_per_unit, thr_out, a_out, b_out, ws, stream);
 }
 
+// ------------------------------------------------------------------------------------------
+// Spatially tiled units, sampled protocol (two collectives): kernels
+// ------------------------------------------------------------------------------------------
+// K1: s_slot hashed-stride samples of every unit's local band -> out[units][s_slot]
+struct TilePivotRanks {
+    int klo, khi, S;
+};
+__device__ __forceinline__ TilePivotRanks tile_pivot_ranks(float q, int64_t n_total, int S) {
+    uint32_t lo, hi;
+    float w;
+    quantile_ranks(q, n_total, lo, hi, w);
+    const float frac = static_cast<float>(lo) / static_cast<float>(n_total > 1 ? n_total - 1 : 1);
+    const float kt = frac * static_cast<float>(S - 1);
+    const float margin = 4.0f * sqrtf(static_cast<float>(S) * frac * (1.0f - frac)) + 4.0f;
+    TilePivotRanks r;
+    r.klo = static_cast<int>(floorf(kt - margin));
+    r.khi = static_cast<int>(ceilf(kt + margin));
+    r.S = S;
+    return r;
+}
+
+// also: the two ranks of the pooled sample (world * s_slot values per unit) whose elements become the bracket pivots
+// (0xffffffff: open end / no select needed)
+__global__ void __launch_bounds__(256) tile_sample_kernel(const float *std_local, int64_t n_local, int64_t units, int s_slot,
+                                                          float *out, uint32_t *rank_in, int world, int64_t n_total, float q01,
+                                                          const float *q01_per_unit) {
+    const int64_t u = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) {
+        const float q = q01_per_unit ? q01_per_unit[u] : q01;
+        const int S = world * s_slot;
+        uint32_t rl = 0xffffffffu, rh = 0xffffffffu;
+        if (unit_mode(q) == kModeThreshold) {
+            const TilePivotRanks t = tile_pivot_ranks(q, n_total, S);
+            if (t.klo > 0) rl = static_cast<uint32_t>(t.klo);
+            if (t.khi < S - 1) rh = static_cast<uint32_t>(t.khi);
+        }
+        rank_in[2 * u] = rl;
+        rank_in[2 * u + 1] = rh;
+    }
+    if (i >= s_slot) return;
+    // hashed stride over the band; a band shorter than the slot is sampled with repetition
+    const uint64_t stride = static_cast<uint64_t>(n_local) >= static_cast<uint64_t>(s_slot) ? static_cast<uint64_t>(n_local) / s_slot : 1u;
+    const uint32_t jit = static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(i) * 0x9E3779B1u) * stride) >> 32);
+    const uint64_t at = (static_cast<uint64_t>(i) * stride + jit) % static_cast<uint64_t>(n_local);
+    out[u * s_slot + i] = __ldg(std_local + u * n_local + at);
+}
+
+// K4: pivots -> GsUnit (sweep state); units that need no select are answered here
+__global__ void tile_pivots_kernel(const float *piv /*[2 * units]*/, GsUnit *st, int64_t units, int64_t n_total, int S, float q01,
+                                   const float *q01_per_unit, float *thr_out) {
+    const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (u >= units) return;
+    const float q = q01_per_unit ? q01_per_unit[u] : q01;
+    const int mode = unit_mode(q);
+    GsUnit g{};
+    if (mode != kModeThreshold) {
+        g.state = 1;
+        thr_out[u] = (mode == kModeOnes) ? -INFINITY : INFINITY;
+    } else {
+        const TilePivotRanks t = tile_pivot_ranks(q, n_total, S);
+        g.plo_f = (t.klo > 0) ? piv[2 * u] : -INFINITY;
+        g.phi_f = (t.khi < S - 1) ? piv[2 * u + 1] : INFINITY;
+        if (g.plo_f != g.plo_f || g.phi_f != g.phi_f) {     // a NaN in the sample: the unit's threshold is NaN
+            g.nan_flag = 1;
+            g.plo_f = -INFINITY;
+            g.phi_f = -INFINITY;                             // empty bracket: nothing to exchange
+        }
+        g.state = 0;
+    }
+    st[u] = g;
+}
+
+// K6: header of this rank's exchange slot: [c_below, c_cand, nan, overflow], candidates follow (written by the sweep)
+__global__ void __launch_bounds__(128) tile_pack_kernel(const GsUnit *st, const uint32_t *below_tile, int tiles, uint32_t *send,
+                                                        int64_t stride, uint32_t cap_x) {
+    __shared__ uint32_t red[4];
+    const int64_t u = blockIdx.x;
+    const int tid = threadIdx.x;
+    uint32_t acc = 0;
+    for (int t = tid; t < tiles; t += 128) acc += below_tile[u * tiles + t];
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid != 0) return;
+    const GsUnit g = st[u];
+    uint32_t *h = send + u * stride;
+    const bool active = g.state == 0u;
+    h[0] = active ? red[0] + red[1] + red[2] + red[3] : 0u;
+    h[1] = active ? (g.c_cand < cap_x ? g.c_cand : cap_x) : 0u;
+    h[2] = g.nan_flag;
+    h[3] = (active && g.c_cand > cap_x) ? 1u : 0u;
+}
+
+// K7: per unit, sum the ranks' headers and line their candidates up in one buffer (one CTA per rank segment); a unit
+// whose bracket does not hold both order statistics (or whose slot overflowed) is counted in *invalid and left out of
+// the final select.  all_x: [units][world][stride]
+__global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, int world, int64_t units, int64_t stride, GsUnit *st,
+                                                         uint32_t *cand_all, int64_t cap_all, int64_t n_total, float q01,
+                                                         const float *q01_per_unit, uint32_t *invalid, float *thr_out) {
+    __shared__ uint32_t sh[4];
+    const int64_t u = blockIdx.y;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const GsUnit g0 = st[u];
+    if (g0.state != 0u) return;       // ones / zeros: answered by tile_pivots_kernel (state is only rewritten below by r == 0,
+                                      // after every CTA of this unit has read it: see the grid-wide ordering note at the launch)
+    if (tid == 0) {
+        uint32_t below = 0, run = 0, nan = g0.nan_flag, ovf = 0, mine = 0;
+        for (int k = 0; k < world; ++k) {
+            const uint32_t *h = all_x + (u * world + k) * stride;
+            if (k == r) mine = run;
+            below += h[0];
+            run += h[1];
+            nan |= h[2];
+            ovf |= h[3];
+        }
+        const float q = q01_per_unit ? q01_per_unit[u] : q01;
+        uint32_t lo, hi;
+        float w;
+        quantile_ranks(q, n_total, lo, hi, w);
+        const bool valid = ovf == 0u && below <= lo && hi < below + run;
+        sh[0] = (valid && nan == 0u) ? 1u : 0u;
+        sh[1] = mine;
+        sh[2] = below;
+        sh[3] = run;
+        if (r == 0) {
+            if (nan != 0u) thr_out[u] = __int_as_float(0x7fc00000);   // any NaN in the unit: NaN threshold (torch.quantile)
+            else if (!valid) atomicAdd(invalid, 1u);                  // the caller falls back to the histogram rounds
+        }
+    }
+    __syncthreads();
+    if (sh[0] == 0u) return;
+    const uint32_t *src = all_x + (u * world + r) * stride;
+    const uint32_t cnt = src[1];
+    uint32_t *dst = cand_all + u * cap_all + sh[1];
+    for (uint32_t i = tid; i < cnt; i += 256) dst[i] = src[4 + i];
+}
+
+// K7b: the merged counts into the select state (after every CTA of tile_merge_kernel has read the old state)
+__global__ void tile_merge_finish_kernel(const uint32_t *all_x, int world, int64_t units, int64_t stride, GsUnit *st, int64_t n_total,
+                                         float q01, const float *q01_per_unit) {
+    const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (u >= units) return;
+    GsUnit g = st[u];
+    if (g.state != 0u) return;
+    uint32_t below = 0, run = 0, nan = g.nan_flag, ovf = 0;
+    for (int k = 0; k < world; ++k) {
+        const uint32_t *h = all_x + (u * world + k) * stride;
+        below += h[0];
+        run += h[1];
+        nan |= h[2];
+        ovf |= h[3];
+    }
+    const float q = q01_per_unit ? q01_per_unit[u] : q01;
+    uint32_t lo, hi;
+    float w;
+    quantile_ranks(q, n_total, lo, hi, w);
+    const bool valid = ovf == 0u && below <= lo && hi < below + run;
+    g.c_below = below;
+    g.c_cand = run;
+    g.nan_flag = nan;
+    if (nan != 0u || !valid) g.state = 1;     // nothing (left) to select for this unit in the cluster select
+    st[u] = g;
+}
+
 static int check_common(int64_t n_per_unit, int64_t units) {
     if (n_per_unit <= 0 || units <= 0) return PIC_ERR_INVALID_ARGUMENT;
     if (n_per_unit > (int64_t(1) << 24)) return PIC_ERR_TOO_LARGE;
@@ -1632,6 +1797,8 @@ struct NcclApi {
     decltype(&ncclCommInitRank) comm_init_rank = nullptr;
     decltype(&ncclCommDestroy) comm_destroy = nullptr;
     decltype(&ncclAllReduce) all_reduce = nullptr;
+    decltype(&ncclAllGather) all_gather = nullptr;
+    decltype(&ncclCommCount) comm_count = nullptr;
     decltype(&ncclGroupStart) group_start = nullptr;
     decltype(&ncclGroupEnd) group_end = nullptr;
     bool ok = false;
@@ -1650,9 +1817,12 @@ const NcclApi &nccl_api() {
         a.comm_init_rank = reinterpret_cast<decltype(a.comm_init_rank)>(dlsym(h, "ncclCommInitRank"));
         a.comm_destroy = reinterpret_cast<decltype(a.comm_destroy)>(dlsym(h, "ncclCommDestroy"));
         a.all_reduce = reinterpret_cast<decltype(a.all_reduce)>(dlsym(h, "ncclAllReduce"));
+        a.all_gather = reinterpret_cast<decltype(a.all_gather)>(dlsym(h, "ncclAllGather"));
+        a.comm_count = reinterpret_cast<decltype(a.comm_count)>(dlsym(h, "ncclCommCount"));
         a.group_start = reinterpret_cast<decltype(a.group_start)>(dlsym(h, "ncclGroupStart"));
         a.group_end = reinterpret_cast<decltype(a.group_end)>(dlsym(h, "ncclGroupEnd"));
-        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.group_start && a.group_end;
+        a.ok = a.get_unique_id && a.comm_init_rank && a.comm_destroy && a.all_reduce && a.all_gather && a.comm_count &&
+               a.group_start && a.group_end;
         return a;
     }();
     return api;
@@ -1729,6 +1899,179 @@ int pic_tiled_select_threshold(const float *std_local, int64_t n_local, int64_t 
     select_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(w.state, w.min_above, units,
                                                                                       thr_out, nullptr, nullptr);
     return launch_status();
+}
+
+// Sampled protocol of the tiled select: TWO collectives instead of four, one pass over the band instead of three.
+//   sample the band -> all-gather the samples -> every rank derives the SAME bracket pivots from the pooled sample ->
+//   one tile-ordered sweep of the band (count below, collect the bracket's elements) -> all-gather counts + candidates ->
+//   every rank selects the exact order statistics among the pooled candidates (cluster select) -> identical thresholds.
+// A bracket that missed (or a slot that overflowed) is detected identically on every rank; then -- and only then -- the
+// histogram-round protocol runs.  That decision needs one 4-byte read-back: this entry synchronises `stream` once and is
+// therefore not CUDA-graph capturable (pic_tiled_select_threshold is).
+namespace {
+struct TiledPlan {
+    int world, s_slot, S, tiles;
+    int64_t cap_x, stride, cap_all;
+    size_t off_send_samp, off_all_samp, off_pooled, off_rank, off_piv, off_st, off_below, off_send_x, off_all_x, off_cand_all,
+        off_invalid, off_rounds, total;
+};
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, TiledPlan &t) {
+    if (world < 1 || world > 64 || units < 1 || n_local < 1) return false;
+    t.world = world;
+    int s_slot = (32768 / world) & ~3;
+    if (s_slot < 1284) s_slot = 1284;                         // pooled sample > kCandMax for every world size
+    while (static_cast<int64_t>(s_slot) * world > kFusedMaxElems) s_slot -= 4;
+    t.s_slot = s_slot;
+    t.S = s_slot * world;
+    if (t.S <= kCandMax) return false;
+    t.tiles = static_cast<int>((n_local + kGsTile - 1) / kGsTile);
+    const double frac = (8.0 * sqrt(t.S * 0.25) + 10.0) / t.S;
+    // exchange sizes must be the same on every rank: they derive from n_total / world, not from this rank's band (a band
+    // much larger than its share overflows its slot -> every rank sees the flag -> histogram rounds)
+    const double share = static_cast<double>((n_total + world - 1) / world);
+    t.cap_x = (static_cast<int64_t>(2.0 * frac * share) + 1024 + 3) & ~int64_t(3);
+    t.stride = t.cap_x + 4;
+    t.cap_all = t.cap_x * world;
+    if (t.cap_all > (int64_t(1) << 31) || units * t.tiles > 0x7fffffffLL) return false;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += up256(bytes); return at; };
+    t.off_send_samp = take(static_cast<size_t>(units) * s_slot * 4);
+    t.off_all_samp = take(static_cast<size_t>(world) * units * s_slot * 4);
+    t.off_pooled = take(static_cast<size_t>(units) * t.S * 4);
+    t.off_rank = take(static_cast<size_t>(units) * 8);
+    t.off_piv = take(static_cast<size_t>(units) * 8);
+    t.off_st = take(static_cast<size_t>(units) * sizeof(GsUnit));
+    t.off_below = take(static_cast<size_t>(units) * t.tiles * 4);
+    t.off_send_x = take(static_cast<size_t>(units) * t.stride * 4 + 64);
+    t.off_all_x = take(static_cast<size_t>(world) * units * t.stride * 4 + 64);
+    t.off_cand_all = take(static_cast<size_t>(units) * t.cap_all * 4);
+    t.off_invalid = take(256);
+    t.off_rounds = take(rounds_ws_bytes(units));
+    t.total = o + 256;
+    return true;
+}
+}  // namespace
+
+size_t pic_tiled_sampled_workspace_bytes(int64_t n_local, int64_t n_total, int64_t units, int world_size) {
+    TiledPlan t;
+    if (!tiled_plan(n_local, n_total, units < 1 ? 1 : units, world_size, t)) return rounds_ws_bytes(units < 1 ? 1 : units);
+    return t.total;
+}
+
+int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                                       const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm_,
+                                       pic_stream_t stream_, int *used_fallback) {
+    int rc = check_common(n_total, units);
+    if (rc != PIC_OK) return rc;
+    if (n_local < 0 || n_local > n_total || (n_local > 0 && !std_local) || !thr_out || !comm_ || !ws) return PIC_ERR_INVALID_ARGUMENT;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    const NcclApi &nc = nccl_api();
+    ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+    int world = 0;
+    rc = nccl_status(nc.comm_count(comm, &world));
+    if (rc != PIC_OK) return rc;
+    if (used_fallback) *used_fallback = 0;
+    TiledPlan t;
+    // every rank must take the same branch: the plan depends on this rank's band, so ranks with unequal bands agree only
+    // when all of them can plan -- bands smaller than a sample slot are the caller's job to avoid (documented)
+    if (n_local < 1 || !aligned4(std_local)) return PIC_ERR_INVALID_ARGUMENT;
+    if (!tiled_plan(n_local, n_total, units, world, t) || ws_bytes < t.total || units > 65535) {
+        if (used_fallback) *used_fallback = 1;
+        return pic_tiled_select_threshold(std_local, n_local, n_total, units, q01, q01_per_unit, thr_out, ws, ws_bytes, comm_, stream_);
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    unsigned char *b = static_cast<unsigned char *>(ws);
+    b = reinterpret_cast<unsigned char *>(up256(reinterpret_cast<size_t>(b)));
+    float *send_samp = reinterpret_cast<float *>(b + t.off_send_samp);
+    float *all_samp = reinterpret_cast<float *>(b + t.off_all_samp);
+    float *pooled = reinterpret_cast<float *>(b + t.off_pooled);
+    uint32_t *rank_in = reinterpret_cast<uint32_t *>(b + t.off_rank);
+    float *piv = reinterpret_cast<float *>(b + t.off_piv);
+    GsUnit *st = reinterpret_cast<GsUnit *>(b + t.off_st);
+    uint32_t *below_tile = reinterpret_cast<uint32_t *>(b + t.off_below);
+    uint32_t *send_x = reinterpret_cast<uint32_t *>(b + t.off_send_x);
+    uint32_t *all_x = reinterpret_cast<uint32_t *>(b + t.off_all_x);
+    uint32_t *cand_all = reinterpret_cast<uint32_t *>(b + t.off_cand_all);
+    uint32_t *invalid = reinterpret_cast<uint32_t *>(b + t.off_invalid);
+    void *rounds_ws = b + t.off_rounds;
+    PIC_CUDA_CHECK(cudaMemsetAsync(invalid, 0, 4, stream));
+    // 1. sample, all-gather, pool
+    tile_sample_kernel<<<dim3((t.s_slot + 255) / 256, static_cast<unsigned>(units)), 256, 0, stream>>>(
+        std_local, n_local, units, t.s_slot, send_samp, rank_in, world, n_total, q01, q01_per_unit);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    // one all-gather per unit inside a group (a single fused NCCL launch): unit u's pooled sample lands contiguously
+    rc = nccl_status(nc.group_start());
+    for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
+        rc = nccl_status(nc.all_gather(send_samp + u * t.s_slot, pooled + u * t.S, static_cast<size_t>(t.s_slot), ncclFloat, comm, stream));
+    {
+        const int rc_end = nccl_status(nc.group_end());
+        if (rc == PIC_OK) rc = rc_end;
+    }
+    if (rc != PIC_OK) return rc;
+    (void)all_samp;
+    // 2. pivots: the two order statistics of every pooled sample (lean select, explicit ranks, two virtual units per unit)
+    {
+        SliceParams sp{};
+        sp.std = pooled; sp.n = t.S; sp.units = units * 2; sp.repeat = 2; sp.rank_in = rank_in;
+        sp.q01 = 0.5f; sp.thr_out = nullptr; sp.a_out = piv; sp.apply_kind = 0;
+        rc = launch_select_lean(sp, stream);
+        if (rc != PIC_OK) return rc;
+    }
+    tile_pivots_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(piv, st, units, n_total, t.S, q01,
+                                                                                      q01_per_unit, thr_out);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    // 3. one sweep of the band: per-tile counts below the bracket, bracket elements straight into the exchange slot
+    GsParams g{};
+    g.std = std_local; g.q01_per_unit = q01_per_unit; g.q01 = q01; g.n = n_local; g.units = units;
+    g.st = st; g.cand = send_x + 4; g.cand_cap = t.stride; g.below_tile = below_tile;
+    g.vec = (n_local % 4 == 0 && aligned16(std_local)) ? 1 : 0;
+    g.thr = thr_out;
+    if (g.vec) gs_sweep_kernel<true, true><<<static_cast<unsigned>(units * t.tiles), kGsThreads, 0, stream>>>(g, t.tiles);
+    else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * t.tiles), kGsThreads, 0, stream>>>(g, t.tiles);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    tile_pack_kernel<<<static_cast<unsigned>(units), 128, 0, stream>>>(st, below_tile, t.tiles, send_x, t.stride,
+                                                                       static_cast<uint32_t>(t.cap_x));
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    // 4. exchange counts + candidates, merge, exact select among the pooled candidates
+    rc = nccl_status(nc.group_start());
+    for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
+        rc = nccl_status(nc.all_gather(send_x + u * t.stride, all_x + u * world * t.stride, static_cast<size_t>(t.stride), ncclUint32,
+                                       comm, stream));
+    {
+        const int rc_end = nccl_status(nc.group_end());
+        if (rc == PIC_OK) rc = rc_end;
+    }
+    if (rc != PIC_OK) return rc;
+    tile_merge_kernel<<<dim3(static_cast<unsigned>(world), static_cast<unsigned>(units)), 256, 0, stream>>>(
+        all_x, world, units, t.stride, st, cand_all, t.cap_all, n_total, q01, q01_per_unit, invalid, thr_out);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    tile_merge_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(all_x, world, units, t.stride, st, n_total,
+                                                                                            q01, q01_per_unit);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    GsParams f{};
+    f.std = nullptr; f.q01_per_unit = q01_per_unit; f.q01 = q01; f.n = n_total; f.units = units;
+    f.st = st; f.cand = cand_all; f.cand_cap = t.cap_all; f.below_tile = nullptr; f.vec = 1;
+    f.thr = thr_out;
+    gs_cluster_select_kernel<true><<<dim3(kClusterCtas, static_cast<unsigned>(units)), kClusterThreads, 0, stream>>>(f, 0);
+    rc = launch_status();
+    if (rc != PIC_OK) return rc;
+    // 5. the one read-back: did every unit's bracket hold?  (identical on all ranks: derived from all-gathered data)
+    uint32_t n_invalid = 0;
+    PIC_CUDA_CHECK(cudaMemcpyAsync(&n_invalid, invalid, 4, cudaMemcpyDeviceToHost, stream));
+    PIC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (n_invalid != 0u) {
+        if (used_fallback) *used_fallback = 1;
+        return pic_tiled_select_threshold(std_local, n_local, n_total, units, q01, q01_per_unit, thr_out, rounds_ws,
+                                          rounds_ws_bytes(units), comm_, stream_);
+    }
+    return PIC_OK;
 }
 
 int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float q01, const float *q01_per_unit,

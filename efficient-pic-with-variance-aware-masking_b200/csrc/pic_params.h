@@ -70,6 +70,8 @@ struct SliceParams {
     int apply_kind;  // 0: select only, 1: mask only, 2: full slice
     int use_stage;   // dynamic shared memory holds the cp.async stage buffer
     int repeat;      // select-only: `repeat` consecutive (virtual) units share one std block (multi-quality select)
+    const uint32_t *rank_in;   // lean select only: explicit 0-based order statistic per (virtual) unit instead of the
+                               // quantile of q01 (0xffffffff: skip the unit); a_out receives the element of that rank
 };
 
 

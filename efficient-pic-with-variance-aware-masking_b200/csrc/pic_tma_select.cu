@@ -1001,7 +1001,7 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
 
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
         const float q = p.q01_per_unit ? p.q01_per_unit[u] : p.q01;
-        const int mode = unit_mode(q);
+        const int mode = p.rank_in ? (p.rank_in[u] == 0xffffffffu ? kModeZeros : kModeThreshold) : unit_mode(q);
         if (mode != kModeThreshold) {
             if (tid == 0) {
                 const float t = (mode == kModeOnes) ? -INFINITY : INFINITY;
@@ -1013,7 +1013,12 @@ __global__ void __launch_bounds__(CT, MINB) select_lean_kernel(const SliceParams
         }
         uint32_t lo, hi;
         float w;
-        quantile_ranks(q, p.n, lo, hi, w);
+        if (p.rank_in) {          // explicit order statistic (pivots of the tiled select's pooled sample)
+            lo = hi = min(p.rank_in[u], static_cast<uint32_t>(n - 1));
+            w = 0.0f;
+        } else {
+            quantile_ranks(q, p.n, lo, hi, w);
+        }
         const float *std_u = p.std + ((p.repeat > 1) ? u / p.repeat : u) * p.n;
         const float4 *s4 = reinterpret_cast<const float4 *>(std_u);
         const int S = sample_size(n);

@@ -94,12 +94,27 @@ class NcclTileComm:
             check(lib().pic_dist_comm_init(raw, rank, world, ctypes.byref(handle)), "pic_dist_comm_init")
         self.handle, self.device, self.world = handle, device, world
         self._ws = None
+        self.fallbacks = 0            # sampled selects that had to run the histogram rounds
 
-    def select_threshold(self, std_local: torch.Tensor, units: int, n_total: int, q01) -> torch.Tensor:
+    def select_threshold(self, std_local: torch.Tensor, units: int, n_total: int, q01, protocol: str = "rounds") -> torch.Tensor:
+        """protocol "rounds": three histogram all-reduces + a min all-reduce, fully asynchronous (graph-capturable);
+        "sampled": two all-gathers and one pass over the band, one stream synchronisation per call (C ABI 1d)."""
+        import ctypes
+
         std_local = ops._require(std_local, "std_local")
         n_local = std_local.numel() // units
         q, qt = ops._q_args(q01, units, std_local.device)
         thr = torch.empty(units, dtype=torch.float32, device=std_local.device)
+        if protocol == "sampled":
+            need = int(lib().pic_tiled_sampled_workspace_bytes(n_local, n_total, units, self.world))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=std_local.device)
+            fb = ctypes.c_int(0)
+            check(lib().pic_tiled_select_threshold_sampled(ops._ptr(std_local), n_local, n_total, units, q, ops._ptr(qt),
+                                                           ops._ptr(thr), ops._ptr(self._ws), self._ws.numel(), self.handle,
+                                                           ops._stream(), ctypes.byref(fb)), "pic_tiled_select_threshold_sampled")
+            self.fallbacks += fb.value
+            return thr
         need = int(lib().pic_tiled_workspace_bytes(units))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=std_local.device)
@@ -124,12 +139,12 @@ def allreduce_min_u32(keys_i32: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def tiled_select_threshold(std_local: Optional[torch.Tensor], units: int, n_total: int, q01, group=None,
-                           backend=None, comm: Optional[NcclTileComm] = None) -> torch.Tensor:
+                           backend=None, comm: Optional[NcclTileComm] = None, protocol: str = "rounds") -> torch.Tensor:
     """Global per-unit quantile threshold of units whose elements are spread over the ranks of
     `group`.  Returns thr [units], bit-identical on every rank.  `comm` (NcclTileComm): the collectives are
     issued inside the library (one host call); otherwise torch.distributed carries them round by round."""
     if comm is not None:
-        return comm.select_threshold(std_local, units, n_total, q01)
+        return comm.select_threshold(std_local, units, n_total, q01, protocol=protocol)
     be = backend if backend is not None else CudaTileBackend(std_local, units)
     be.begin(n_total, q01)
     for rnd in range(3):
@@ -142,7 +157,7 @@ def tiled_select_threshold(std_local: Optional[torch.Tensor], units: int, n_tota
 
 def tiled_slice_forward(y_top, y_base, mu, std, units: int, n_total: int, pr, scale_table=None, noise=None,
                         group=None, scale_bound: float = 0.11, lik_bound: float = 1e-9,
-                        want=("mask", "y_hat", "lik"), comm: Optional[NcclTileComm] = None) -> dict:
+                        want=("mask", "y_hat", "lik"), comm: Optional[NcclTileComm] = None, protocol: str = "rounds") -> dict:
     """One progressive slice of spatially tiled units: all-reduced threshold + local apply."""
     q01 = pr if isinstance(pr, torch.Tensor) else ops.pr_to_q01(pr)
     mode_scalar = None if isinstance(q01, torch.Tensor) else q01
@@ -150,7 +165,7 @@ def tiled_slice_forward(y_top, y_base, mu, std, units: int, n_total: int, pr, sc
         # ones / zeros short-circuit: no threshold, no collective
         return ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise,
                                  scale_bound=scale_bound, lik_bound=lik_bound, want=want)
-    thr = tiled_select_threshold(std, units, n_total, q01, group, comm=comm)
+    thr = tiled_select_threshold(std, units, n_total, q01, group, comm=comm, protocol=protocol)
     res = ops.slice_forward(y_top, y_base, mu, std, units, q01, scale_table, noise=noise, thr_in=thr,
                             scale_bound=scale_bound, lik_bound=lik_bound, want=want)
     res["thr"] = thr

@@ -160,6 +160,21 @@ int pic_tiled_select_threshold(const float *std_local, int64_t n_local, int64_t 
                                size_t ws_bytes, void *comm, pic_stream_t stream);
 
 /*
+ * (1d) Sampled protocol of (1c): TWO collectives instead of four and ONE pass over the band instead of three.  Every
+ * rank samples its band, the samples are all-gathered, every rank derives the same bracket pivots from the pooled
+ * sample, sweeps its band once (count below, collect the bracket's elements), the counts and candidates are
+ * all-gathered and every rank selects the exact order statistics among them: thresholds are bit-identical to (1c) and to
+ * the single-device select.  A bracket that missed or an exchange slot that overflowed is seen identically by every
+ * rank; only then the histogram rounds of (1c) run (*used_fallback = 1).  That decision needs a 4-byte read-back: this
+ * entry synchronises `stream` once per call and cannot be captured in a CUDA graph ((1c) can).  Every rank must hold
+ * at least one element of each unit.  ws: pic_tiled_sampled_workspace_bytes().
+ */
+size_t pic_tiled_sampled_workspace_bytes(int64_t n_local, int64_t n_total, int64_t units, int world_size);
+int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                                       const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm,
+                                       pic_stream_t stream, int *used_fallback);
+
+/*
  * (2) ChannelMask.forward / ProgMask (channel_mask.py:18-49, 89-151): mask = (std >= thr) as
  * f32 {0,1}; ones / zeros for the sentinels.  thr_out nullable.
  */

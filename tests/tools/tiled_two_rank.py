@@ -74,6 +74,24 @@ def main():
     both_nan = np.isnan(lik) & np.isnan(want)       # the NaN scale of unit 2 gives a NaN likelihood on both sides
     close = np.abs(lik - want) <= LIK_RTOL * np.abs(want) + LIK_ATOL
     check(bool(np.all(close | both_nan)), "likelihood of the band out of tolerance")
+    # sampled protocol (C ABI 1d) on the same ragged, tie-heavy bands: exact whether or not it has to fall back
+    thr_s = pdist.tiled_select_threshold(std_l, units, n, q, comm=comm, protocol="sampled")
+    check(np.array_equal(thr_s.cpu().numpy(), ref["thr"], equal_nan=True), "sampled protocol (ragged bands) != oracle")
+    # ... and on equal bands of larger iid units, where it must NOT fall back
+    units2, n2 = 5, world * 262144
+    rng2 = np.random.default_rng(77)
+    std2 = trained_like(rng2, (units2, n2))[3]
+    std2[3, 5] = np.nan
+    prs2 = [0.5, 2.5, 5.0, 9.0, 7.0]
+    b2 = n2 // world
+    std2_l = torch.from_numpy(np.ascontiguousarray(std2[:, rank * b2:(rank + 1) * b2])).to(dev)
+    before = comm.fallbacks
+    thr2 = pdist.tiled_select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm, protocol="sampled")
+    want2 = np.asarray([po.quantile(std2[u], np.float32(1.0 - prs2[u] * 0.1))[0] for u in range(units2)], np.float32)
+    check(np.array_equal(thr2.cpu().numpy(), want2, equal_nan=True), f"sampled protocol (equal bands) != oracle: {thr2.cpu().numpy()} vs {want2}")
+    check(comm.fallbacks == before, f"sampled protocol fell back on iid equal bands ({comm.fallbacks - before})")
+    thr2r = pdist.tiled_select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm)
+    check(np.array_equal(thr2r.cpu().numpy(), want2, equal_nan=True), "rounds protocol (equal bands) != oracle")
     comm.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
