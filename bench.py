@@ -720,15 +720,34 @@ def bench_tile(cx: Ctx):
         same_ranks = all(bool(torch.equal(every[0], e)) for e in every)
         rec["thresholds_equal"] = {"library_nccl_vs_torch_distributed": same, "across_ranks": same_ranks}
 
-        protocol = os.environ.get("PIC_TILED_PROTOCOL", "sampled")
+        protocol = os.environ.get("PIC_TILED_PROTOCOL", "p2p")
         t_s = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm, protocol="sampled")
         rec["thresholds_equal"]["sampled_vs_rounds"] = bool(torch.equal(t_s, t_c))
+        if protocol == "p2p":
+            try:
+                comm.enable_p2p(n, units)
+                t_p = comm.select_threshold(std, units, n, q_all, protocol="p2p")
+                rec["thresholds_equal"]["p2p_vs_rounds"] = bool(torch.equal(t_p, t_c))
+            except Exception as exc:  # no CUDA IPC between the ranks (all ranks fail together): NCCL carries the exchange
+                rec["p2p_unavailable"] = f"{type(exc).__name__}: {exc}"
+                protocol = "rounds"
 
         def step():
-            thr = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm, protocol=protocol)
+            if protocol == "p2p":
+                thr = comm.select_threshold(std, units, n, q_all, protocol="p2p", check_status=False)
+            else:
+                thr = pdist.tiled_select_threshold(std, units, n, q_all, comm=comm, protocol=protocol)
             ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, thr_in=thr, want=want, out=outs)
         rec["protocol"] = protocol
-        if protocol == "sampled":
+        if protocol == "p2p":
+            rec["launches_per_step"] = 11    # sample, exchange, pivot select, pivots, sweep, pack, exchange, merge x2, cluster select, apply
+            rec["collectives_per_step"] = 0
+            rec["collective"] = ("two peer-memory exchanges (NVLink stores into the peers' CUDA IPC windows + flags) issued by "
+                                 "libpic_latent.so's own kernels: the bands' samples, then bracket counts + candidates; no NCCL "
+                                 "call, no host synchronisation, validity word checked after the timed region")
+            graph = bool(args.graph) and os.environ.get("PIC_TILED_GRAPH", "1") != "0"
+            comm._p2p_status.zero_()
+        elif protocol == "sampled":
             rec["launches_per_step"] = 9     # sample, pool, pivot select, pivots, sweep, pack, merge, cluster select, apply
             rec["collectives_per_step"] = 2
             rec["collective"] = ("ncclAllGather of the bands' samples + ncclAllGather of the bracket counts and candidates, issued "
@@ -748,6 +767,8 @@ def bench_tile(cx: Ctx):
                 "whole_step_frac": (units * n_local * wl["bytes_per_elem"] / (t["own_ms"] * 1e-3) / 1e9) / cx.hbm})
     if comm is not None:
         rec["sampled_selects_that_fell_back"] = comm.fallbacks
+        if rec.get("protocol") == "p2p":
+            rec["p2p_status_after_timed_region"] = comm.p2p_status()     # 0: every bracket held, no exchange timed out
         comm.close()
     del y_top, y_base, mu, std, outs
     torch.cuda.empty_cache()

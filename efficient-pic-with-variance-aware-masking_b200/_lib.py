@@ -61,6 +61,10 @@ SIGNATURES = {
     "pic_tiled_select_threshold": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "pic_tiled_sampled_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "pic_tiled_select_threshold_sampled": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "pic_dist_p2p_region_bytes": (C.c_int, [_i64, _i64, _i32, _vp, _vp]),
+    "pic_dist_p2p_init": (C.c_int, [_vp, _i32, _sz, _sz, _vp]),
+    "pic_dist_p2p_destroy": (C.c_int, [_vp]),
+    "pic_tiled_select_threshold_p2p": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "pic_channel_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pic_attention_mask": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "pic_lrp_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),

@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/pic_latent.h"
 #include "pic_math.cuh"
 #include "pic_fast.cuh"
@@ -1618,6 +1620,84 @@ __global__ void tile_merge_finish_kernel(const uint32_t *all_x, int world, int64
     st[u] = g;
 }
 
+// ---- peer-memory exchange (NVLink / NVSwitch stores into the peers' windows) --------------------------------------------
+// Every rank owns one window (cudaMalloc + CUDA IPC, mapped by all peers).  Layout: [flags 2 x 64 u32][local words]
+// [region 0 | region 1].  An exchange = every rank stores its rows into the same place of EVERY window (its own
+// included), fences, then raises flags[region][rank] = epoch in every window and waits until all of its own flags reached
+// the epoch.  Two regions alternate within one tiled select, which is what makes reuse safe without double buffering:
+// a rank can only start writing region R of call k+1 after it saw the peers' flags of the exchange in between, and a
+// peer raises those only after (in stream order) it finished reading region R of call k.
+constexpr int kP2pMaxWorld = 64;
+constexpr size_t kP2pFlagsOff = 0, kP2pLocalOff = 1024, kP2pDataOff = 4096;
+struct P2pLocal {
+    uint32_t done[2], epoch[2], error, pad[3];
+};
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// rows: `units` rows of this rank; row u = src[u * src_stride ..], `fixed_words` words long, or (fixed_words < 0) a
+// 4-word header + src[u * src_stride + 1] payload words.  Lands at window[dst_off + (u * world + rank) * dst_stride].
+// grid (chunks, units); the last CTA to finish signals and waits.
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(unsigned char *const *windows, int rank, int world, int region,
+                                                            const uint32_t *src, int64_t src_stride, int fixed_words,
+                                                            size_t dst_off, int64_t dst_stride, uint32_t *status) {
+    __shared__ uint32_t sh_last;
+    const int64_t u = blockIdx.y;
+    const int tid = threadIdx.x;
+    const uint32_t *row = src + u * src_stride;
+    int64_t words = fixed_words >= 0 ? fixed_words : 4 + static_cast<int64_t>(row[1]);
+    if (words > dst_stride) words = dst_stride;
+    const int64_t vecs = (words + 3) >> 2;     // rows are 16-byte aligned and padded to whole vectors on both sides
+    const int64_t v0 = vecs * blockIdx.x / gridDim.x, v1 = vecs * (blockIdx.x + 1) / gridDim.x;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(row);
+    for (int k = 0; k < world; ++k) {
+        int p = rank + k;                       // start with the own window, every rank walks the peers in a different order
+        if (p >= world) p -= world;
+        uint4 *d4 = reinterpret_cast<uint4 *>(windows[p] + dst_off) + ((u * world + rank) * dst_stride >> 2);
+        for (int64_t i = v0 + tid; i < v1; i += 256) d4[i] = __ldg(s4 + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    P2pLocal *loc = reinterpret_cast<P2pLocal *>(windows[rank] + kP2pLocalOff);
+    if (tid == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        sh_last = (atomicAdd(&loc->done[region], 1u) == total - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sh_last == 0u) return;
+    __threadfence_system();
+    const uint32_t e = loc->epoch[region] + 1u;
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<uint32_t *>(windows[tid] + kP2pFlagsOff) + region * kP2pMaxWorld + rank, e);
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(windows[rank] + kP2pFlagsOff) + region * kP2pMaxWorld + tid;
+        const uint64_t t0 = global_ns();
+        while (static_cast<int32_t>(ld_acquire_sys(mine) - e) < 0) {
+            __nanosleep(100);
+            if (global_ns() - t0 > 4000000000ull) {    // a peer never arrived (4 s): report instead of hanging the GPU
+                atomicAdd(&loc->error, 1u);
+                if (status) atomicAdd(status, 0x10000u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        loc->done[region] = 0u;
+        loc->epoch[region] = e;
+    }
+}
+
 static int check_common(int64_t n_per_unit, int64_t units) {
     if (n_per_unit <= 0 || units <= 0) return PIC_ERR_INVALID_ARGUMENT;
     if (n_per_unit > (int64_t(1) << 24)) return PIC_ERR_TOO_LARGE;
@@ -1959,9 +2039,27 @@ size_t pic_tiled_sampled_workspace_bytes(int64_t n_local, int64_t n_total, int64
     return t.total;
 }
 
-int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
-                                       const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm_,
-                                       pic_stream_t stream_, int *used_fallback) {
+namespace {
+struct P2pCtx {
+    int rank = 0, world = 1;
+    size_t bytes = 0, region_bytes[2] = {0, 0};
+    unsigned char *window[kP2pMaxWorld] = {};   // window[rank] is this rank's own allocation
+    unsigned char **windows_dev = nullptr;      // the same table in device memory
+    ncclComm_t comm = nullptr;
+    int device = 0;
+};
+
+// all ranks meet here (used around window setup / teardown only)
+int p2p_barrier(const P2pCtx &c, uint32_t *scratch_dev, cudaStream_t stream) {
+    const int rc = nccl_status(nccl_api().all_reduce(scratch_dev, scratch_dev, 1, ncclUint32, ncclSum, c.comm, stream));
+    if (rc != PIC_OK) return rc;
+    PIC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return PIC_OK;
+}
+
+int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                       const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm_, P2pCtx *p2p,
+                       uint32_t *status_dev, pic_stream_t stream_, int *used_fallback) {
     int rc = check_common(n_total, units);
     if (rc != PIC_OK) return rc;
     if (n_local < 0 || n_local > n_total || (n_local > 0 && !std_local) || !thr_out || !comm_ || !ws) return PIC_ERR_INVALID_ARGUMENT;
@@ -1976,7 +2074,14 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
     // every rank must take the same branch: the plan depends on this rank's band, so ranks with unequal bands agree only
     // when all of them can plan -- bands smaller than a sample slot are the caller's job to avoid (documented)
     if (n_local < 1 || !aligned4(std_local)) return PIC_ERR_INVALID_ARGUMENT;
-    if (!tiled_plan(n_local, n_total, units, world, t) || ws_bytes < t.total || units > 65535) {
+    const bool planned = tiled_plan(n_local, n_total, units, world, t) && ws_bytes >= t.total && units <= 65535;
+    const size_t x1_bytes = planned ? static_cast<size_t>(units) * t.S * 4 : 0;
+    const size_t x2_bytes = planned ? static_cast<size_t>(world) * units * t.stride * 4 : 0;
+    if (p2p) {
+        // peer-memory transport: no host decision inside (graph capturable), so "cannot plan" is an error, not a fallback
+        if (!planned || p2p->world != world || x1_bytes > p2p->region_bytes[0] || x2_bytes > p2p->region_bytes[1] || !status_dev)
+            return PIC_ERR_WORKSPACE;
+    } else if (!planned) {
         if (used_fallback) *used_fallback = 1;
         return pic_tiled_select_threshold(std_local, n_local, n_total, units, q01, q01_per_unit, thr_out, ws, ws_bytes, comm_, stream_);
     }
@@ -1984,7 +2089,6 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
     unsigned char *b = static_cast<unsigned char *>(ws);
     b = reinterpret_cast<unsigned char *>(up256(reinterpret_cast<size_t>(b)));
     float *send_samp = reinterpret_cast<float *>(b + t.off_send_samp);
-    float *all_samp = reinterpret_cast<float *>(b + t.off_all_samp);
     float *pooled = reinterpret_cast<float *>(b + t.off_pooled);
     uint32_t *rank_in = reinterpret_cast<uint32_t *>(b + t.off_rank);
     float *piv = reinterpret_cast<float *>(b + t.off_piv);
@@ -1995,22 +2099,35 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
     uint32_t *cand_all = reinterpret_cast<uint32_t *>(b + t.off_cand_all);
     uint32_t *invalid = reinterpret_cast<uint32_t *>(b + t.off_invalid);
     void *rounds_ws = b + t.off_rounds;
-    PIC_CUDA_CHECK(cudaMemsetAsync(invalid, 0, 4, stream));
-    // 1. sample, all-gather, pool
+    size_t x1_off = 0, x2_off = 0;
+    if (p2p) {
+        x1_off = kP2pDataOff;
+        x2_off = kP2pDataOff + p2p->region_bytes[0];
+        pooled = reinterpret_cast<float *>(p2p->window[p2p->rank] + x1_off);
+        all_x = reinterpret_cast<uint32_t *>(p2p->window[p2p->rank] + x2_off);
+        invalid = status_dev;                       // the caller owns (and clears) the status word
+    } else {
+        PIC_CUDA_CHECK(cudaMemsetAsync(invalid, 0, 4, stream));
+    }
+    // 1. sample the band (and derive the pivot ranks of the pooled sample), exchange: unit u's pooled sample is contiguous
     tile_sample_kernel<<<dim3((t.s_slot + 255) / 256, static_cast<unsigned>(units)), 256, 0, stream>>>(
         std_local, n_local, units, t.s_slot, send_samp, rank_in, world, n_total, q01, q01_per_unit);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
-    // one all-gather per unit inside a group (a single fused NCCL launch): unit u's pooled sample lands contiguously
-    rc = nccl_status(nc.group_start());
-    for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
-        rc = nccl_status(nc.all_gather(send_samp + u * t.s_slot, pooled + u * t.S, static_cast<size_t>(t.s_slot), ncclFloat, comm, stream));
-    {
+    if (p2p) {
+        p2p_exchange_kernel<<<dim3(4, static_cast<unsigned>(units)), 256, 0, stream>>>(
+            p2p->windows_dev, p2p->rank, world, 0, reinterpret_cast<const uint32_t *>(send_samp), t.s_slot, t.s_slot, x1_off,
+            t.s_slot, status_dev);
+        rc = launch_status();
+    } else {
+        // one all-gather per unit inside a group (a single fused NCCL launch)
+        rc = nccl_status(nc.group_start());
+        for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
+            rc = nccl_status(nc.all_gather(send_samp + u * t.s_slot, pooled + u * t.S, static_cast<size_t>(t.s_slot), ncclFloat, comm, stream));
         const int rc_end = nccl_status(nc.group_end());
         if (rc == PIC_OK) rc = rc_end;
     }
     if (rc != PIC_OK) return rc;
-    (void)all_samp;
     // 2. pivots: the two order statistics of every pooled sample (lean select, explicit ranks, two virtual units per unit)
     {
         SliceParams sp{};
@@ -2038,11 +2155,16 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
     rc = launch_status();
     if (rc != PIC_OK) return rc;
     // 4. exchange counts + candidates, merge, exact select among the pooled candidates
-    rc = nccl_status(nc.group_start());
-    for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
-        rc = nccl_status(nc.all_gather(send_x + u * t.stride, all_x + u * world * t.stride, static_cast<size_t>(t.stride), ncclUint32,
-                                       comm, stream));
-    {
+    if (p2p) {
+        // only the header and the candidates that exist cross the links (NCCL has to move the whole fixed-size slot)
+        p2p_exchange_kernel<<<dim3(8, static_cast<unsigned>(units)), 256, 0, stream>>>(
+            p2p->windows_dev, p2p->rank, world, 1, send_x, t.stride, -1, x2_off, t.stride, status_dev);
+        rc = launch_status();
+    } else {
+        rc = nccl_status(nc.group_start());
+        for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
+            rc = nccl_status(nc.all_gather(send_x + u * t.stride, all_x + u * world * t.stride, static_cast<size_t>(t.stride), ncclUint32,
+                                           comm, stream));
         const int rc_end = nccl_status(nc.group_end());
         if (rc == PIC_OK) rc = rc_end;
     }
@@ -2062,6 +2184,7 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
     gs_cluster_select_kernel<true><<<dim3(kClusterCtas, static_cast<unsigned>(units)), kClusterThreads, 0, stream>>>(f, 0);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
+    if (p2p) return PIC_OK;     // the caller reads the status word at its next synchronisation point
     // 5. the one read-back: did every unit's bracket hold?  (identical on all ranks: derived from all-gathered data)
     uint32_t n_invalid = 0;
     PIC_CUDA_CHECK(cudaMemcpyAsync(&n_invalid, invalid, 4, cudaMemcpyDeviceToHost, stream));
@@ -2072,6 +2195,153 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
                                           rounds_ws_bytes(units), comm_, stream_);
     }
     return PIC_OK;
+}
+}  // namespace
+
+int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                                       const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *comm_,
+                                       pic_stream_t stream_, int *used_fallback) {
+    return tiled_sampled_impl(std_local, n_local, n_total, units, q01, q01_per_unit, thr_out, ws, ws_bytes, comm_, nullptr, nullptr,
+                              stream_, used_fallback);
+}
+
+// ---- peer-memory transport of the sampled protocol ---------------------------------------------------------------------
+int pic_dist_p2p_region_bytes(int64_t n_total, int64_t units, int world_size, size_t *sample_bytes, size_t *cand_bytes) {
+    TiledPlan t;
+    if (!sample_bytes || !cand_bytes || n_total < 1 || units < 1) return PIC_ERR_INVALID_ARGUMENT;
+    if (!tiled_plan(n_total, n_total, units, world_size, t)) return PIC_ERR_TOO_LARGE;
+    *sample_bytes = up256(static_cast<size_t>(units) * t.S * 4);
+    *cand_bytes = up256(static_cast<size_t>(world_size) * units * t.stride * 4);
+    return PIC_OK;
+}
+
+int pic_dist_p2p_init(void *comm_, int rank, size_t sample_bytes, size_t cand_bytes, void **p2p_out) {
+    if (!comm_ || !p2p_out || rank < 0) return PIC_ERR_INVALID_ARGUMENT;
+    if (!nccl_api().ok) return PIC_ERR_CUDA;
+    *p2p_out = nullptr;
+    P2pCtx *c = new P2pCtx();
+    c->comm = static_cast<ncclComm_t>(comm_);
+    int rc = nccl_status(nccl_api().comm_count(c->comm, &c->world));
+    if (rc != PIC_OK || c->world > kP2pMaxWorld || rank >= c->world) {
+        delete c;
+        return rc != PIC_OK ? rc : PIC_ERR_INVALID_ARGUMENT;
+    }
+    c->rank = rank;
+    c->region_bytes[0] = up256(sample_bytes);
+    c->region_bytes[1] = up256(cand_bytes);
+    c->bytes = kP2pDataOff + c->region_bytes[0] + c->region_bytes[1];
+    cudaStream_t stream = nullptr;
+    unsigned char *handles_dev = nullptr;
+    auto fail = [&](int code) {
+        for (int p = 0; p < c->world; ++p)
+            if (p != c->rank && c->window[p]) cudaIpcCloseMemHandle(c->window[p]);
+        if (c->window[c->rank]) cudaFree(c->window[c->rank]);
+        if (c->windows_dev) cudaFree(c->windows_dev);
+        if (handles_dev) cudaFree(handles_dev);
+        if (stream) cudaStreamDestroy(stream);
+        delete c;
+        return code;
+    };
+#define PIC_P2P_TRY(call)                                                  \
+    do {                                                                   \
+        const cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) {                                           \
+            pic::g_last_cuda_error = static_cast<int>(e_);                 \
+            (void)cudaGetLastError();                                      \
+            return fail(PIC_ERR_CUDA);                                     \
+        }                                                                  \
+    } while (0)
+    PIC_P2P_TRY(cudaGetDevice(&c->device));
+    PIC_P2P_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaIpcMemHandle_t mine;
+    // a rank that cannot allocate or export still has to take part in the all-gather below (else the peers hang): it
+    // sends zeros and every rank fails together
+    cudaError_t exported = cudaMalloc(&c->window[c->rank], c->bytes);
+    if (exported == cudaSuccess) exported = cudaMemsetAsync(c->window[c->rank], 0, c->bytes, stream);
+    if (exported == cudaSuccess) exported = cudaStreamSynchronize(stream);
+    if (exported == cudaSuccess) exported = cudaIpcGetMemHandle(&mine, c->window[c->rank]);
+    if (exported != cudaSuccess) {
+        pic::g_last_cuda_error = static_cast<int>(exported);
+        (void)cudaGetLastError();
+        memset(&mine, 0, sizeof(mine));
+    }
+    const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;     // handle + "ok" marker
+    PIC_P2P_TRY(cudaMalloc(&handles_dev, hb * (c->world + 1)));
+    unsigned char send[sizeof(cudaIpcMemHandle_t) + 8] = {};
+    memcpy(send, &mine, sizeof(mine));
+    send[sizeof(mine)] = exported == cudaSuccess ? 1 : 0;
+    PIC_P2P_TRY(cudaMemcpyAsync(handles_dev + hb * c->world, send, hb, cudaMemcpyHostToDevice, stream));
+    rc = nccl_status(nccl_api().all_gather(handles_dev + hb * c->world, handles_dev, hb, ncclUint8, c->comm, stream));
+    if (rc != PIC_OK) return fail(rc);
+    std::vector<unsigned char> all(hb * c->world);
+    PIC_P2P_TRY(cudaMemcpyAsync(all.data(), handles_dev, all.size(), cudaMemcpyDeviceToHost, stream));
+    PIC_P2P_TRY(cudaStreamSynchronize(stream));
+    bool every_ok = true;
+    for (int p = 0; p < c->world; ++p) every_ok = every_ok && all[hb * p + sizeof(cudaIpcMemHandle_t)] == 1;
+    int open_failed = 0;
+    if (every_ok) {
+        for (int p = 0; p < c->world && !open_failed; ++p) {
+            if (p == c->rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + hb * p, sizeof(h));
+            void *ptr = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                pic::g_last_cuda_error = static_cast<int>(e);
+                (void)cudaGetLastError();
+                open_failed = 1;
+            } else {
+                c->window[p] = static_cast<unsigned char *>(ptr);
+            }
+        }
+    }
+    // agree on the outcome: nobody may start storing into a window some rank failed to map (and then freed)
+    uint32_t *flag_dev = reinterpret_cast<uint32_t *>(handles_dev);
+    const uint32_t bad = (every_ok && !open_failed) ? 0u : 1u;
+    PIC_P2P_TRY(cudaMemcpyAsync(flag_dev, &bad, 4, cudaMemcpyHostToDevice, stream));
+    rc = p2p_barrier(*c, flag_dev, stream);
+    if (rc != PIC_OK) return fail(rc);
+    uint32_t bad_total = 0;
+    PIC_P2P_TRY(cudaMemcpy(&bad_total, flag_dev, 4, cudaMemcpyDeviceToHost));
+    if (bad_total != 0u) return fail(PIC_ERR_CUDA);
+    PIC_P2P_TRY(cudaMalloc(&c->windows_dev, sizeof(unsigned char *) * kP2pMaxWorld));
+    PIC_P2P_TRY(cudaMemcpy(c->windows_dev, c->window, sizeof(unsigned char *) * kP2pMaxWorld, cudaMemcpyHostToDevice));
+    cudaFree(handles_dev);
+    cudaStreamDestroy(stream);
+#undef PIC_P2P_TRY
+    *p2p_out = c;
+    return PIC_OK;
+}
+
+int pic_dist_p2p_destroy(void *p2p_) {
+    if (!p2p_) return PIC_OK;
+    P2pCtx *c = static_cast<P2pCtx *>(p2p_);
+    int rc = PIC_OK;
+    uint32_t *word = nullptr;
+    // peers may still be storing into this window: meet first, unmap, meet again, then free
+    if (cudaMalloc(&word, 4) == cudaSuccess && cudaMemset(word, 0, 4) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        rc = p2p_barrier(*c, word, nullptr);
+        for (int p = 0; p < c->world; ++p)
+            if (p != c->rank && c->window[p]) cudaIpcCloseMemHandle(c->window[p]);
+        if (rc == PIC_OK) rc = p2p_barrier(*c, word, nullptr);
+    } else {
+        rc = PIC_ERR_CUDA;
+    }
+    if (word) cudaFree(word);
+    if (c->window[c->rank]) cudaFree(c->window[c->rank]);
+    if (c->windows_dev) cudaFree(c->windows_dev);
+    delete c;
+    return rc;
+}
+
+int pic_tiled_select_threshold_p2p(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                                   const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *p2p_,
+                                   uint32_t *status_dev, pic_stream_t stream_) {
+    if (!p2p_) return PIC_ERR_INVALID_ARGUMENT;
+    P2pCtx *c = static_cast<P2pCtx *>(p2p_);
+    return tiled_sampled_impl(std_local, n_local, n_total, units, q01, q01_per_unit, thr_out, ws, ws_bytes, c->comm, c, status_dev,
+                              stream_, nullptr);
 }
 
 int pic_channel_mask(const float *std, int64_t n_per_unit, int64_t units, float q01, const float *q01_per_unit,

@@ -94,17 +94,63 @@ class NcclTileComm:
             check(lib().pic_dist_comm_init(raw, rank, world, ctypes.byref(handle)), "pic_dist_comm_init")
         self.handle, self.device, self.world = handle, device, world
         self._ws = None
-        self.fallbacks = 0            # sampled selects that had to run the histogram rounds
+        self.fallbacks = 0            # sampled / p2p selects that had to run the histogram rounds
+        self.rank = rank
+        self._p2p = None
+        self._p2p_status = None
 
-    def select_threshold(self, std_local: torch.Tensor, units: int, n_total: int, q01, protocol: str = "rounds") -> torch.Tensor:
+    def enable_p2p(self, n_total_max: int, units_max: int) -> None:
+        """Collective over the communicator: allocate this rank's peer-memory window (sized for the largest tiled unit /
+        slice count it will serve), exchange the CUDA IPC handles and map the peers' windows (C ABI 1e).  Single node."""
+        import ctypes
+
+        if self._p2p is not None:
+            return
+        a, b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        check(lib().pic_dist_p2p_region_bytes(n_total_max, units_max, self.world, ctypes.byref(a), ctypes.byref(b)),
+              "pic_dist_p2p_region_bytes")
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().pic_dist_p2p_init(self.handle, self.rank, a.value, b.value, ctypes.byref(handle)), "pic_dist_p2p_init")
+        self._p2p = handle
+        self._p2p_status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def p2p_status(self) -> int:
+        """Status word of the p2p selects issued since it was last cleared (synchronises): low 16 bits = units whose
+        bracket missed, higher bits = exchange waits that timed out.  Non-zero: those thresholds are not valid."""
+        return int(self._p2p_status.item()) & 0xFFFFFFFF
+
+    def select_threshold(self, std_local: torch.Tensor, units: int, n_total: int, q01, protocol: str = "rounds",
+                         check_status: bool = True) -> torch.Tensor:
         """protocol "rounds": three histogram all-reduces + a min all-reduce, fully asynchronous (graph-capturable);
-        "sampled": two all-gathers and one pass over the band, one stream synchronisation per call (C ABI 1d)."""
+        "sampled": two all-gathers and one pass over the band, one stream synchronisation per call (C ABI 1d);
+        "p2p": the sampled protocol over peer-memory windows (enable_p2p first; C ABI 1e) -- with check_status=False
+        nothing synchronises (graph-capturable) and the caller reads p2p_status() at its next synchronisation point."""
         import ctypes
 
         std_local = ops._require(std_local, "std_local")
         n_local = std_local.numel() // units
         q, qt = ops._q_args(q01, units, std_local.device)
         thr = torch.empty(units, dtype=torch.float32, device=std_local.device)
+        if protocol == "p2p":
+            if self._p2p is None:
+                raise RuntimeError("NcclTileComm.enable_p2p(n_total_max, units_max) has to run (on every rank) first")
+            need = int(lib().pic_tiled_sampled_workspace_bytes(n_local, n_total, units, self.world))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=std_local.device)
+            if check_status:
+                self._p2p_status.zero_()
+            check(lib().pic_tiled_select_threshold_p2p(ops._ptr(std_local), n_local, n_total, units, q, ops._ptr(qt), ops._ptr(thr),
+                                                       ops._ptr(self._ws), self._ws.numel(), self._p2p,
+                                                       ops._ptr(self._p2p_status), ops._stream()), "pic_tiled_select_threshold_p2p")
+            if check_status:
+                status = self.p2p_status()
+                if status >> 16:
+                    raise RuntimeError("peer-memory exchange timed out: a rank of the tiled select never arrived")
+                if status:
+                    self.fallbacks += 1
+                    return self.select_threshold(std_local, units, n_total, q01, protocol="rounds")
+            return thr
         if protocol == "sampled":
             need = int(lib().pic_tiled_sampled_workspace_bytes(n_local, n_total, units, self.world))
             if self._ws is None or self._ws.numel() < need:
@@ -124,6 +170,11 @@ class NcclTileComm:
         return thr
 
     def close(self) -> None:
+        if self._p2p is not None:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                check(lib().pic_dist_p2p_destroy(self._p2p), "pic_dist_p2p_destroy")
+            self._p2p = None
         if self.handle:
             torch.cuda.synchronize(self.device)
             check(lib().pic_dist_comm_destroy(self.handle), "pic_dist_comm_destroy")

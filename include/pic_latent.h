@@ -175,6 +175,27 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
                                        pic_stream_t stream, int *used_fallback);
 
 /*
+ * (1e) The sampled protocol of (1d) over PEER MEMORY instead of NCCL: every rank owns one window (cudaMalloc exported
+ * with CUDA IPC, mapped by all peers of the node); an exchange is a kernel that stores this rank's rows straight into
+ * every peer's window over NVLink / NVSwitch, raises a flag there and waits for the peers' flags -- a few microseconds
+ * instead of a collective launch, and only the candidates that exist cross the links.  Nothing on the host happens
+ * between the steps and nothing is read back, so the whole select (and the apply behind it) captures into one CUDA
+ * graph.  The price is that the validity check moves to the caller: *status_dev (device word, the caller zeroes it) counts
+ * the units whose bracket missed or whose slot overflowed in its low 16 bits and adds 0x10000 per exchange wait that
+ * timed out (a peer that never arrived: 4 s); when it is non-zero after the caller's next synchronisation the
+ * thresholds of that call are not valid and (1c) has to be run instead -- every rank sees the same low 16 bits.
+ * pic_dist_p2p_init / _destroy are collective over `comm` (they exchange the IPC handles and meet through it); the
+ * regions are sized by pic_dist_p2p_region_bytes for the LARGEST (n_total, units) the window will serve.  One select at
+ * a time per window; all ranks issue the same sequence of selects.  Single node only.
+ */
+int pic_dist_p2p_region_bytes(int64_t n_total, int64_t units, int world_size, size_t *sample_bytes, size_t *cand_bytes);
+int pic_dist_p2p_init(void *comm, int rank, size_t sample_bytes, size_t cand_bytes, void **p2p_out);
+int pic_dist_p2p_destroy(void *p2p);
+int pic_tiled_select_threshold_p2p(const float *std_local, int64_t n_local, int64_t n_total, int64_t units, float q01,
+                                   const float *q01_per_unit, float *thr_out, void *ws, size_t ws_bytes, void *p2p,
+                                   uint32_t *status_dev, pic_stream_t stream);
+
+/*
  * (2) ChannelMask.forward / ProgMask (channel_mask.py:18-49, 89-151): mask = (std >= thr) as
  * f32 {0,1}; ones / zeros for the sentinels.  thr_out nullable.
  */

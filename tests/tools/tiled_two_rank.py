@@ -92,6 +92,21 @@ def main():
     check(comm.fallbacks == before, f"sampled protocol fell back on iid equal bands ({comm.fallbacks - before})")
     thr2r = pdist.tiled_select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm)
     check(np.array_equal(thr2r.cpu().numpy(), want2, equal_nan=True), "rounds protocol (equal bands) != oracle")
+    # peer-memory transport of the sampled protocol (C ABI 1e): same thresholds, no NCCL call in the select itself
+    comm.enable_p2p(max(n, n2), max(units, units2))
+    for rep in range(3):                              # windows are reused: epochs have to line up call after call
+        thr_p = pdist.tiled_select_threshold(std_l, units, n, q, comm=comm, protocol="p2p")
+        check(np.array_equal(thr_p.cpu().numpy(), ref["thr"], equal_nan=True), f"p2p protocol (ragged bands, call {rep}) != oracle")
+        before = comm.fallbacks
+        thr2p = pdist.tiled_select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm, protocol="p2p")
+        check(np.array_equal(thr2p.cpu().numpy(), want2, equal_nan=True), f"p2p protocol (equal bands, call {rep}) != oracle")
+        check(comm.fallbacks == before, "p2p protocol fell back on iid equal bands")
+    # asynchronous form, as a CUDA graph would replay it: status word read once at the end
+    comm._p2p_status.zero_()
+    outs_async = [comm.select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), protocol="p2p", check_status=False)
+                  for _ in range(20)]
+    check(comm.p2p_status() == 0, f"p2p status word {comm.p2p_status():#x} after 20 back-to-back selects")
+    check(all(np.array_equal(o.cpu().numpy(), want2, equal_nan=True) for o in outs_async), "back-to-back p2p selects != oracle")
     comm.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
