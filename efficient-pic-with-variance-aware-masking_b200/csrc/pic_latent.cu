@@ -1549,20 +1549,19 @@ __global__ void __launch_bounds__(128) tile_pack_kernel(const GsUnit *st, const 
     h[3] = (active && g.c_cand > cap_x) ? 1u : 0u;
 }
 
-// K7: per unit, sum the ranks' headers and line their candidates up in one buffer (one CTA per rank segment); a unit
-// whose bracket does not hold both order statistics (or whose slot overflowed) is counted in *invalid and left out of
-// the final select.  all_x: [units][world][stride]
-__global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, int world, int64_t units, int64_t stride, GsUnit *st,
-                                                         uint32_t *cand_all, int64_t cap_all, int64_t n_total, float q01,
+// K7: per unit, sum the ranks' headers and line their candidates up in one buffer (`split` CTAs per rank segment); a
+// unit whose bracket does not hold both order statistics (or whose slot overflowed) is counted in *invalid and left out
+// of the final select.  all_x: [units][world][stride].  Only the headers are read (never st[u], which CTA (0, u) updates).
+__global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, int world, int split, int64_t units, int64_t stride,
+                                                         GsUnit *st, uint32_t *cand_all, int64_t cap_all, int64_t n_total, float q01,
                                                          const float *q01_per_unit, uint32_t *invalid, float *thr_out) {
-    __shared__ uint32_t sh[4];
+    __shared__ uint32_t sh[2];
     const int64_t u = blockIdx.y;
-    const int r = blockIdx.x, tid = threadIdx.x;
-    const GsUnit g0 = st[u];
-    if (g0.state != 0u) return;       // ones / zeros: answered by tile_pivots_kernel (state is only rewritten below by r == 0,
-                                      // after every CTA of this unit has read it: see the grid-wide ordering note at the launch)
+    const int r = blockIdx.x / split, part = blockIdx.x - r * split, tid = threadIdx.x;
+    const float q = q01_per_unit ? q01_per_unit[u] : q01;
+    if (unit_mode(q) != kModeThreshold) return;     // ones / zeros: answered by tile_pivots_kernel
     if (tid == 0) {
-        uint32_t below = 0, run = 0, nan = g0.nan_flag, ovf = 0, mine = 0;
+        uint32_t below = 0, run = 0, nan = 0, ovf = 0, mine = 0;
         for (int k = 0; k < world; ++k) {
             const uint32_t *h = all_x + (u * world + k) * stride;
             if (k == r) mine = run;
@@ -1571,53 +1570,30 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, 
             nan |= h[2];
             ovf |= h[3];
         }
-        const float q = q01_per_unit ? q01_per_unit[u] : q01;
         uint32_t lo, hi;
         float w;
         quantile_ranks(q, n_total, lo, hi, w);
         const bool valid = ovf == 0u && below <= lo && hi < below + run;
         sh[0] = (valid && nan == 0u) ? 1u : 0u;
         sh[1] = mine;
-        sh[2] = below;
-        sh[3] = run;
-        if (r == 0) {
+        if (blockIdx.x == 0) {
             if (nan != 0u) thr_out[u] = __int_as_float(0x7fc00000);   // any NaN in the unit: NaN threshold (torch.quantile)
             else if (!valid) atomicAdd(invalid, 1u);                  // the caller falls back to the histogram rounds
+            GsUnit *g = st + u;
+            g->c_below = below;
+            g->c_cand = run;
+            g->nan_flag = nan;
+            g->state = (nan != 0u || !valid) ? 1u : 0u;               // 1: nothing (left) to select in the cluster select
         }
     }
     __syncthreads();
     if (sh[0] == 0u) return;
     const uint32_t *src = all_x + (u * world + r) * stride;
     const uint32_t cnt = src[1];
+    const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * part / split);
+    const uint32_t i1 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * (part + 1) / split);
     uint32_t *dst = cand_all + u * cap_all + sh[1];
-    for (uint32_t i = tid; i < cnt; i += 256) dst[i] = src[4 + i];
-}
-
-// K7b: the merged counts into the select state (after every CTA of tile_merge_kernel has read the old state)
-__global__ void tile_merge_finish_kernel(const uint32_t *all_x, int world, int64_t units, int64_t stride, GsUnit *st, int64_t n_total,
-                                         float q01, const float *q01_per_unit) {
-    const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (u >= units) return;
-    GsUnit g = st[u];
-    if (g.state != 0u) return;
-    uint32_t below = 0, run = 0, nan = g.nan_flag, ovf = 0;
-    for (int k = 0; k < world; ++k) {
-        const uint32_t *h = all_x + (u * world + k) * stride;
-        below += h[0];
-        run += h[1];
-        nan |= h[2];
-        ovf |= h[3];
-    }
-    const float q = q01_per_unit ? q01_per_unit[u] : q01;
-    uint32_t lo, hi;
-    float w;
-    quantile_ranks(q, n_total, lo, hi, w);
-    const bool valid = ovf == 0u && below <= lo && hi < below + run;
-    g.c_below = below;
-    g.c_cand = run;
-    g.nan_flag = nan;
-    if (nan != 0u || !valid) g.state = 1;     // nothing (left) to select for this unit in the cluster select
-    st[u] = g;
+    for (uint32_t i = i0 + tid; i < i1; i += 256) dst[i] = src[4 + i];
 }
 
 // ---- peer-memory exchange (NVLink / NVSwitch stores into the peers' windows) --------------------------------------------
@@ -1649,14 +1625,43 @@ __device__ __forceinline__ uint64_t global_ns() {
 // rows: `units` rows of this rank; row u = src[u * src_stride ..], `fixed_words` words long, or (fixed_words < 0) a
 // 4-word header + src[u * src_stride + 1] payload words.  Lands at window[dst_off + (u * world + rank) * dst_stride].
 // grid (chunks, units); the last CTA to finish signals and waits.
+// Pack mode (st != nullptr): the row's 4-word header [c_below, c_cand, nan, overflow] is computed here from the sweep's
+// per-tile counts instead of being read from src (tile_pack_kernel folded into the exchange).
+struct P2pPack {
+    const GsUnit *st;
+    const uint32_t *below_tile;
+    int tiles;
+    uint32_t cap_x;
+};
 __global__ void __launch_bounds__(256) p2p_exchange_kernel(unsigned char *const *windows, int rank, int world, int region,
                                                             const uint32_t *src, int64_t src_stride, int fixed_words,
-                                                            size_t dst_off, int64_t dst_stride, uint32_t *status) {
+                                                            size_t dst_off, int64_t dst_stride, uint32_t *status, P2pPack pk) {
     __shared__ uint32_t sh_last;
+    __shared__ uint32_t red[8];
+    __shared__ uint4 sh_head;
     const int64_t u = blockIdx.y;
     const int tid = threadIdx.x;
     const uint32_t *row = src + u * src_stride;
-    int64_t words = fixed_words >= 0 ? fixed_words : 4 + static_cast<int64_t>(row[1]);
+    int64_t words;
+    if (pk.st) {
+        uint32_t acc = 0;
+        for (int t = tid; t < pk.tiles; t += 256) acc += pk.below_tile[u * pk.tiles + t];
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            const GsUnit g = pk.st[u];
+            const bool active = g.state == 0u;
+            uint32_t below = 0;
+            for (int k = 0; k < 8; ++k) below += red[k];
+            sh_head = make_uint4(active ? below : 0u, active ? (g.c_cand < pk.cap_x ? g.c_cand : pk.cap_x) : 0u, g.nan_flag,
+                                 (active && g.c_cand > pk.cap_x) ? 1u : 0u);
+        }
+        __syncthreads();
+        words = 4 + static_cast<int64_t>(sh_head.y);
+    } else {
+        words = fixed_words >= 0 ? fixed_words : 4 + static_cast<int64_t>(row[1]);
+    }
     if (words > dst_stride) words = dst_stride;
     const int64_t vecs = (words + 3) >> 2;     // rows are 16-byte aligned and padded to whole vectors on both sides
     const int64_t v0 = vecs * blockIdx.x / gridDim.x, v1 = vecs * (blockIdx.x + 1) / gridDim.x;
@@ -1665,18 +1670,20 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(unsigned char *const 
         int p = rank + k;                       // start with the own window, every rank walks the peers in a different order
         if (p >= world) p -= world;
         uint4 *d4 = reinterpret_cast<uint4 *>(windows[p] + dst_off) + ((u * world + rank) * dst_stride >> 2);
-        for (int64_t i = v0 + tid; i < v1; i += 256) d4[i] = __ldg(s4 + i);
+        for (int64_t i = v0 + tid; i < v1; i += 256) d4[i] = (pk.st && i == 0) ? sh_head : __ldg(s4 + i);
     }
-    __threadfence_system();
     __syncthreads();
     P2pLocal *loc = reinterpret_cast<P2pLocal *>(windows[rank] + kP2pLocalOff);
     if (tid == 0) {
+        // bar.sync ordered the CTA's stores before this thread; its system-scope fence is cumulative over them
+        __threadfence_system();
         const uint32_t total = gridDim.x * gridDim.y;
         sh_last = (atomicAdd(&loc->done[region], 1u) == total - 1u) ? 1u : 0u;
     }
     __syncthreads();
     if (sh_last == 0u) return;
-    __threadfence_system();
+    if (tid == 0) __threadfence_system();
+    __syncthreads();
     const uint32_t e = loc->epoch[region] + 1u;
     if (tid < world) {
         st_release_sys(reinterpret_cast<uint32_t *>(windows[tid] + kP2pFlagsOff) + region * kP2pMaxWorld + rank, e);
@@ -2117,7 +2124,7 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
     if (p2p) {
         p2p_exchange_kernel<<<dim3(4, static_cast<unsigned>(units)), 256, 0, stream>>>(
             p2p->windows_dev, p2p->rank, world, 0, reinterpret_cast<const uint32_t *>(send_samp), t.s_slot, t.s_slot, x1_off,
-            t.s_slot, status_dev);
+            t.s_slot, status_dev, P2pPack{nullptr, nullptr, 0, 0u});
         rc = launch_status();
     } else {
         // one all-gather per unit inside a group (a single fused NCCL launch)
@@ -2150,17 +2157,19 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
     else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * t.tiles), kGsThreads, 0, stream>>>(g, t.tiles);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
-    tile_pack_kernel<<<static_cast<unsigned>(units), 128, 0, stream>>>(st, below_tile, t.tiles, send_x, t.stride,
-                                                                       static_cast<uint32_t>(t.cap_x));
-    rc = launch_status();
-    if (rc != PIC_OK) return rc;
     // 4. exchange counts + candidates, merge, exact select among the pooled candidates
     if (p2p) {
-        // only the header and the candidates that exist cross the links (NCCL has to move the whole fixed-size slot)
+        // only the header (computed inside the exchange kernel) and the candidates that exist cross the links (NCCL has
+        // to move the whole fixed-size slot)
         p2p_exchange_kernel<<<dim3(8, static_cast<unsigned>(units)), 256, 0, stream>>>(
-            p2p->windows_dev, p2p->rank, world, 1, send_x, t.stride, -1, x2_off, t.stride, status_dev);
+            p2p->windows_dev, p2p->rank, world, 1, send_x, t.stride, -1, x2_off, t.stride, status_dev,
+            P2pPack{st, below_tile, t.tiles, static_cast<uint32_t>(t.cap_x)});
         rc = launch_status();
     } else {
+        tile_pack_kernel<<<static_cast<unsigned>(units), 128, 0, stream>>>(st, below_tile, t.tiles, send_x, t.stride,
+                                                                           static_cast<uint32_t>(t.cap_x));
+        rc = launch_status();
+        if (rc != PIC_OK) return rc;
         rc = nccl_status(nc.group_start());
         for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
             rc = nccl_status(nc.all_gather(send_x + u * t.stride, all_x + u * world * t.stride, static_cast<size_t>(t.stride), ncclUint32,
@@ -2169,12 +2178,9 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
         if (rc == PIC_OK) rc = rc_end;
     }
     if (rc != PIC_OK) return rc;
-    tile_merge_kernel<<<dim3(static_cast<unsigned>(world), static_cast<unsigned>(units)), 256, 0, stream>>>(
-        all_x, world, units, t.stride, st, cand_all, t.cap_all, n_total, q01, q01_per_unit, invalid, thr_out);
-    rc = launch_status();
-    if (rc != PIC_OK) return rc;
-    tile_merge_finish_kernel<<<static_cast<unsigned>((units + 127) / 128), 128, 0, stream>>>(all_x, world, units, t.stride, st, n_total,
-                                                                                            q01, q01_per_unit);
+    const int split = world >= 32 ? 1 : 32 / world;
+    tile_merge_kernel<<<dim3(static_cast<unsigned>(world * split), static_cast<unsigned>(units)), 256, 0, stream>>>(
+        all_x, world, split, units, t.stride, st, cand_all, t.cap_all, n_total, q01, q01_per_unit, invalid, thr_out);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
     GsParams f{};
