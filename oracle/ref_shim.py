@@ -3,8 +3,12 @@
 Used only in the build container (where /root/reference exists) by
 ``oracle/gen_golden.py`` to generate the golden vectors committed under
 ``tests/golden/`` and by ``oracle/gen_golden_model*.py`` / ``gen_golden_codec.py`` (model- and coder-derived vectors); ``tests/test_oracle_golden.py`` pins the C
-restatement.  Nothing on the product path, in ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` imports this file: /root/reference does not exist on the GPU box.
+restatement.  Nothing on the product path, in ``-m gpu`` tests or ``smoke()``
+imports this file: /root/reference does not exist on the GPU box.  The one other
+user is ``bench.py --impl reference``: when (and only when) ``PIC_REFERENCE_ROOT``
+points at a visible reference tree -- the build container -- it also times the
+reference's own torch code for the path through this loader (``torch_reference``
+in its JSON line); on the GPU box that leg is skipped.
 
 The reference modules on the hot path are
 
