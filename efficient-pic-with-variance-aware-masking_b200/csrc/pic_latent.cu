@@ -2003,7 +2003,11 @@ struct TiledPlan {
         off_invalid, off_rounds, total;
 };
 size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, TiledPlan &t) {
+// slot_margin: how many times its fair share of the bracket's elements one rank's slot can hold (bands of real images
+// differ: a threshold inside the texture of the lower half puts most candidates into the lower bands).  The NCCL
+// transport moves whole slots, so it stays at 2; the peer-memory transport moves only what exists and takes 4.
+constexpr double kSlotMarginNccl = 2.0, kSlotMarginP2p = 4.0;
+bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, double slot_margin, TiledPlan &t) {
     if (world < 1 || world > 64 || units < 1 || n_local < 1) return false;
     t.world = world;
     int s_slot = (32768 / world) & ~3;
@@ -2017,7 +2021,9 @@ bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, Tile
     // exchange sizes must be the same on every rank: they derive from n_total / world, not from this rank's band (a band
     // much larger than its share overflows its slot -> every rank sees the flag -> histogram rounds)
     const double share = static_cast<double>((n_total + world - 1) / world);
-    t.cap_x = (static_cast<int64_t>(2.0 * frac * share) + 1024 + 3) & ~int64_t(3);
+    int64_t cap = static_cast<int64_t>(slot_margin * frac * share) + 1024;
+    if (cap > static_cast<int64_t>(share) + 1024) cap = static_cast<int64_t>(share) + 1024;
+    t.cap_x = (cap + 3) & ~int64_t(3);
     t.stride = t.cap_x + 4;
     t.cap_all = t.cap_x * world;
     if (t.cap_all > (int64_t(1) << 31) || units * t.tiles > 0x7fffffffLL) return false;
@@ -2042,7 +2048,7 @@ bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, Tile
 
 size_t pic_tiled_sampled_workspace_bytes(int64_t n_local, int64_t n_total, int64_t units, int world_size) {
     TiledPlan t;
-    if (!tiled_plan(n_local, n_total, units < 1 ? 1 : units, world_size, t)) return rounds_ws_bytes(units < 1 ? 1 : units);
+    if (!tiled_plan(n_local, n_total, units < 1 ? 1 : units, world_size, kSlotMarginP2p, t)) return rounds_ws_bytes(units < 1 ? 1 : units);
     return t.total;
 }
 
@@ -2081,7 +2087,8 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
     // every rank must take the same branch: the plan depends on this rank's band, so ranks with unequal bands agree only
     // when all of them can plan -- bands smaller than a sample slot are the caller's job to avoid (documented)
     if (n_local < 1 || !aligned4(std_local)) return PIC_ERR_INVALID_ARGUMENT;
-    const bool planned = tiled_plan(n_local, n_total, units, world, t) && ws_bytes >= t.total && units <= 65535;
+    const bool planned = tiled_plan(n_local, n_total, units, world, p2p ? kSlotMarginP2p : kSlotMarginNccl, t) && ws_bytes >= t.total &&
+                         units <= 65535;
     const size_t x1_bytes = planned ? static_cast<size_t>(units) * t.S * 4 : 0;
     const size_t x2_bytes = planned ? static_cast<size_t>(world) * units * t.stride * 4 : 0;
     if (p2p) {
@@ -2215,7 +2222,7 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
 int pic_dist_p2p_region_bytes(int64_t n_total, int64_t units, int world_size, size_t *sample_bytes, size_t *cand_bytes) {
     TiledPlan t;
     if (!sample_bytes || !cand_bytes || n_total < 1 || units < 1) return PIC_ERR_INVALID_ARGUMENT;
-    if (!tiled_plan(n_total, n_total, units, world_size, t)) return PIC_ERR_TOO_LARGE;
+    if (!tiled_plan(n_total, n_total, units, world_size, kSlotMarginP2p, t)) return PIC_ERR_TOO_LARGE;
     *sample_bytes = up256(static_cast<size_t>(units) * t.S * 4);
     *cand_bytes = up256(static_cast<size_t>(world_size) * units * t.stride * 4);
     return PIC_OK;

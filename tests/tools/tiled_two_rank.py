@@ -101,6 +101,18 @@ def main():
         thr2p = pdist.tiled_select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm, protocol="p2p")
         check(np.array_equal(thr2p.cpu().numpy(), want2, equal_nan=True), f"p2p protocol (equal bands, call {rep}) != oracle")
         check(comm.fallbacks == before, "p2p protocol fell back on iid equal bands")
+    # bands of different content (a threshold inside the last band's value range puts most of the bracket's elements
+    # there): the exchange slot holds up to 4 x a rank's fair share, so up to 4 ranks this must not fall back
+    std3 = std2.copy()
+    for r in range(world):
+        std3[:, r * b2:(r + 1) * b2] *= np.float32(1.0 + 0.75 * r)
+    std3_l = torch.from_numpy(np.ascontiguousarray(std3[:, rank * b2:(rank + 1) * b2])).to(dev)
+    want3 = np.asarray([po.quantile(std3[u], np.float32(1.0 - prs2[u] * 0.1))[0] for u in range(units2)], np.float32)
+    before = comm.fallbacks
+    thr3 = pdist.tiled_select_threshold(std3_l, units2, n2, ops.q01_tensor(prs2, dev), comm=comm, protocol="p2p")
+    check(np.array_equal(thr3.cpu().numpy(), want3, equal_nan=True), "p2p protocol (bands of different content) != oracle")
+    if world <= 4:
+        check(comm.fallbacks == before, f"p2p protocol fell back on bands of different content ({comm.fallbacks - before})")
     # asynchronous form, as a CUDA graph would replay it: status word read once at the end
     comm._p2p_status.zero_()
     outs_async = [comm.select_threshold(std2_l, units2, n2, ops.q01_tensor(prs2, dev), protocol="p2p", check_status=False)
