@@ -1553,8 +1553,8 @@ __global__ void __launch_bounds__(128) tile_pack_kernel(const GsUnit *st, const 
 // unit whose bracket does not hold both order statistics (or whose slot overflowed) is counted in *invalid and left out
 // of the final select.  all_x: [units][world][stride].  Only the headers are read (never st[u], which CTA (0, u) updates).
 __global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, int world, int split, int64_t units, int64_t stride,
-                                                         GsUnit *st, uint32_t *cand_all, int64_t cap_all, int64_t n_total, float q01,
-                                                         const float *q01_per_unit, uint32_t *invalid, float *thr_out) {
+                                                         GsUnit *st, uint32_t *cand_all, int64_t cap_all, uint32_t cap_x, int64_t n_total,
+                                                         float q01, const float *q01_per_unit, uint32_t *invalid, float *thr_out) {
     __shared__ uint32_t sh[2];
     const int64_t u = blockIdx.y;
     const int r = blockIdx.x / split, part = blockIdx.x - r * split, tid = threadIdx.x;
@@ -1566,9 +1566,9 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, 
             const uint32_t *h = all_x + (u * world + k) * stride;
             if (k == r) mine = run;
             below += h[0];
-            run += h[1];
+            run += h[1] < cap_x ? h[1] : cap_x;      // a header that never arrived (exchange time-out) must not index past the slot
             nan |= h[2];
-            ovf |= h[3];
+            ovf |= h[3] | (h[1] > cap_x ? 1u : 0u);
         }
         uint32_t lo, hi;
         float w;
@@ -1589,7 +1589,7 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, 
     __syncthreads();
     if (sh[0] == 0u) return;
     const uint32_t *src = all_x + (u * world + r) * stride;
-    const uint32_t cnt = src[1];
+    const uint32_t cnt = src[1] < cap_x ? src[1] : cap_x;
     const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * part / split);
     const uint32_t i1 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * (part + 1) / split);
     uint32_t *dst = cand_all + u * cap_all + sh[1];
@@ -2187,7 +2187,8 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
     if (rc != PIC_OK) return rc;
     const int split = world >= 32 ? 1 : 32 / world;
     tile_merge_kernel<<<dim3(static_cast<unsigned>(world * split), static_cast<unsigned>(units)), 256, 0, stream>>>(
-        all_x, world, split, units, t.stride, st, cand_all, t.cap_all, n_total, q01, q01_per_unit, invalid, thr_out);
+        all_x, world, split, units, t.stride, st, cand_all, t.cap_all, static_cast<uint32_t>(t.cap_x), n_total, q01, q01_per_unit,
+        invalid, thr_out);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
     GsParams f{};

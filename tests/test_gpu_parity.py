@@ -689,6 +689,62 @@ def test_library_issued_nccl_select_world_size_1(pic, dev):
     assert L.pic_dist_comm_destroy(comm) == 0
 
 
+def test_sampled_and_peer_memory_select_world_size_1(pic, dev):
+    """The sampled tiled select (C ABI 1d, NCCL all-gathers) and its peer-memory transport (1e: CUDA IPC window, the
+    library's own exchange kernel, no host synchronisation) on a one-rank communicator: thresholds equal the oracle's,
+    incl. ties, a NaN unit, the ones / zeros sentinels and an unaligned, ragged band; the window is reused over several
+    selects; the status word stays 0.  (N > 1: tests/test_gpu_multi.py and bench.py's tile8192 workload.)"""
+    import ctypes
+
+    L = pic.lib()
+    ident = (ctypes.c_ubyte * 128)()
+    comm = ctypes.c_void_p()
+    if L.pic_dist_unique_id(ident) != 0 or L.pic_dist_comm_init(ident, 0, 1, ctypes.byref(comm)) != 0 or not comm.value:
+        pytest.skip(f"NCCL could not create a one-rank communicator here (code {L.pic_last_cuda_error()})")
+    rng = np.random.default_rng(31)
+    stream = torch.cuda.current_stream().cuda_stream
+    cases = [(6, 262144, [0.5, 5, 9.9999, 0, 10, 7.3]), (3, 3 * 40000 + 7, [2.5, 1e-4, 6.0])]
+    a, b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    assert L.pic_dist_p2p_region_bytes(max(c[1] for c in cases), max(c[0] for c in cases), 1, ctypes.byref(a), ctypes.byref(b)) == 0
+    p2p = ctypes.c_void_p()
+    rc = L.pic_dist_p2p_init(comm, 0, a.value, b.value, ctypes.byref(p2p))
+    assert rc == 0 and p2p.value, f"pic_dist_p2p_init: {rc} (cuda {L.pic_last_cuda_error()})"
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    for rep in range(2):
+        for units, n, prs in cases:
+            std = trained_like(rng, (units, n))[3]
+            std[:, ::3] = np.round(std[:, ::3] * 8) / 8
+            std[1, :] = 0.5
+            std[2, 11] = np.nan
+            ts = T(std, dev)
+            q = pic.ops.q01_tensor(prs, dev)
+            ws = torch.empty(int(L.pic_tiled_sampled_workspace_bytes(n, n, units, 1)), dtype=torch.uint8, device=dev)
+            _, want = po.channel_mask(std, prs)
+            thr = torch.full((units,), -7.0, dtype=torch.float32, device=dev)
+            fb = ctypes.c_int(0)
+            assert L.pic_tiled_select_threshold_sampled(ts.data_ptr(), n, n, units, 0.0, q.data_ptr(), thr.data_ptr(), ws.data_ptr(),
+                                                        ws.numel(), comm, stream, ctypes.byref(fb)) == 0
+            torch.cuda.synchronize()
+            assert np.array_equal(N(thr), want, equal_nan=True), ("sampled", units, n, fb.value)
+            thr.fill_(-7.0)
+            assert L.pic_tiled_select_threshold_p2p(ts.data_ptr(), n, n, units, 0.0, q.data_ptr(), thr.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), p2p, status.data_ptr(), stream) == 0
+            torch.cuda.synchronize()
+            assert int(status.item()) >> 16 == 0, "exchange timed out"
+            if int(status.item()) == 0:       # bracket held: the thresholds are final (else the caller re-runs 1c)
+                assert np.array_equal(N(thr), want, equal_nan=True), ("p2p", units, n)
+            status.zero_()
+    # a window too small for the request is refused, not overrun
+    big_n = 4 * max(c[1] for c in cases)
+    ws = torch.empty(int(L.pic_tiled_sampled_workspace_bytes(big_n, big_n, 6, 1)), dtype=torch.uint8, device=dev)
+    big = torch.ones(6 * big_n, dtype=torch.float32, device=dev)
+    thr = torch.empty(6, dtype=torch.float32, device=dev)
+    assert L.pic_tiled_select_threshold_p2p(big.data_ptr(), big_n, big_n, 6, 0.5, None, thr.data_ptr(), ws.data_ptr(), ws.numel(), p2p,
+                                            status.data_ptr(), stream) == pic._lib.PIC_ERR_WORKSPACE
+    assert L.pic_dist_p2p_destroy(p2p) == 0
+    assert L.pic_dist_comm_destroy(comm) == 0
+
+
 def test_randomised_slice_configurations(pic, dev):
     """40 seeded random configurations (units, ragged n across all three launch plans, per-unit qualities incl. the
     ones / zeros sentinels, optional y_base / noise / table, output subsets, input distributions) vs the oracle."""
