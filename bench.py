@@ -740,7 +740,7 @@ def bench_tile(cx: Ctx):
             ops.slice_forward(y_top, y_base, mu, std, units, q_all, cx.table, thr_in=thr, want=want, out=outs)
         rec["protocol"] = protocol
         if protocol == "p2p":
-            rec["launches_per_step"] = 11    # sample, exchange, pivot select, pivots, sweep, pack, exchange, merge x2, cluster select, apply
+            rec["launches_per_step"] = 8     # sample+exchange, pivot select, pivots, sweep, exchange(+pack), merge, cluster select, apply
             rec["collectives_per_step"] = 0
             rec["collective"] = ("two peer-memory exchanges (NVLink stores into the peers' CUDA IPC windows + flags) issued by "
                                  "libpic_latent.so's own kernels: the bands' samples, then bracket counts + candidates; no NCCL "

@@ -125,31 +125,14 @@ __global__ void __launch_bounds__(kGsThreads, 5) gs_pivot_kernel(const GsParams 
     if (tid == 0) p.st[u] = st;
 }
 
-// RAW: candidates are stored as float bits (input of the histogram rounds) instead of ordered keys.
-// One CTA per 8192-element tile: the tile is parked in shared memory while it is classified (one hit bit per
-// element in a register), then ONE global reservation per CTA places the tile's bracket elements in the unit's
-// candidate buffer (per-warp reservations serialise on the unit's counter once units are millions of elements).
-template <bool VEC, bool RAW>
-__global__ void __launch_bounds__(kGsThreads, 4) gs_sweep_kernel(const GsParams p, int tiles_per_unit) {
+// Classification of one tile (shared by gs_sweep_kernel and the tiled select's fused sweep + exchange kernel): parks
+// the tile in shared memory, counts the elements below the bracket, sets one hit bit per bracket element
+// (VEC: bit 4*i + e <-> element e of float4 (i * THREADS + tid); scalar: bit i <-> element i * THREADS + tid).
+template <bool VEC>
+__device__ __forceinline__ void gs_classify_tile(const float *base, int len, float plo_f, float phi_f, float4 *park4,
+                                                 uint32_t &below, uint32_t &hits, bool &has_nan) {
     constexpr int THREADS = kGsThreads;
-    constexpr int WARPS = THREADS / 32;
-    static_assert(kGsTile == 32 * THREADS, "one hit bit per element and thread");
-    __shared__ __align__(16) float4 park4[kGsTile / 4];   // 32 KB: the CTA's tile
-    __shared__ uint32_t warp_off[WARPS + 1], warp_below[WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t u = blockIdx.x / tiles_per_unit;
-    const int tile = blockIdx.x - static_cast<int>(u) * tiles_per_unit;
-    GsUnit *st = p.st + u;
-    if (st->state != 0u) return;
-    const float plo_f = st->plo_f, phi_f = st->phi_f;
-    const int64_t begin = static_cast<int64_t>(tile) * kGsTile;
-    const int len = static_cast<int>(min(static_cast<int64_t>(kGsTile), p.n - begin));
-    const float *base = p.std + u * p.n + begin;
-    uint32_t *cand = p.cand + u * p.cand_cap;
-    const uint32_t cap = static_cast<uint32_t>(p.cand_cap);
-    const float *parkf = reinterpret_cast<const float *>(park4);
-    uint32_t below = 0, hits = 0;
-    bool has_nan = false;
+    const int tid = threadIdx.x;
     if (VEC) {   // bit 4*i + e  <->  element e of float4 (i * THREADS + tid)
         const int nvec = len >> 2;   // VEC: n % 4 == 0, so every tile is whole float4s
         const uint64_t pol_last = policy_evict_last();
@@ -204,6 +187,34 @@ __global__ void __launch_bounds__(kGsThreads, 4) gs_sweep_kernel(const GsParams 
             }
         }
     }
+}
+
+// RAW: candidates are stored as float bits (input of the histogram rounds) instead of ordered keys.
+// One CTA per 8192-element tile: the tile is parked in shared memory while it is classified (one hit bit per
+// element in a register), then ONE global reservation per CTA places the tile's bracket elements in the unit's
+// candidate buffer (per-warp reservations serialise on the unit's counter once units are millions of elements).
+template <bool VEC, bool RAW>
+__global__ void __launch_bounds__(kGsThreads, 4) gs_sweep_kernel(const GsParams p, int tiles_per_unit) {
+    constexpr int THREADS = kGsThreads;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(kGsTile == 32 * THREADS, "one hit bit per element and thread");
+    __shared__ __align__(16) float4 park4[kGsTile / 4];   // 32 KB: the CTA's tile
+    __shared__ uint32_t warp_off[WARPS + 1], warp_below[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u = blockIdx.x / tiles_per_unit;
+    const int tile = blockIdx.x - static_cast<int>(u) * tiles_per_unit;
+    GsUnit *st = p.st + u;
+    if (st->state != 0u) return;
+    const float plo_f = st->plo_f, phi_f = st->phi_f;
+    const int64_t begin = static_cast<int64_t>(tile) * kGsTile;
+    const int len = static_cast<int>(min(static_cast<int64_t>(kGsTile), p.n - begin));
+    const float *base = p.std + u * p.n + begin;
+    uint32_t *cand = p.cand + u * p.cand_cap;
+    const uint32_t cap = static_cast<uint32_t>(p.cand_cap);
+    const float *parkf = reinterpret_cast<const float *>(park4);
+    uint32_t below = 0, hits = 0;
+    bool has_nan = false;
+    gs_classify_tile<VEC>(base, len, plo_f, phi_f, park4, below, hits, has_nan);
     // CTA-wide reservation: warp scan -> per-warp offsets -> one atomicAdd on the unit's counter
     const uint32_t cnt = static_cast<uint32_t>(__popc(hits));
     uint32_t incl = cnt;

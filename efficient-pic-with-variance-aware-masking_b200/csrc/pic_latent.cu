@@ -1476,6 +1476,14 @@ __device__ __forceinline__ TilePivotRanks tile_pivot_ranks(float q, int64_t n_to
     return r;
 }
 
+// sample i of unit u's band: hashed stride over the band; a band shorter than the slot is sampled with repetition
+__device__ __forceinline__ float tile_sample_value(const float *std_local, int64_t n_local, int64_t u, int s_slot, int i) {
+    const uint64_t stride = static_cast<uint64_t>(n_local) >= static_cast<uint64_t>(s_slot) ? static_cast<uint64_t>(n_local) / s_slot : 1u;
+    const uint32_t jit = static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(i) * 0x9E3779B1u) * stride) >> 32);
+    const uint64_t at = (static_cast<uint64_t>(i) * stride + jit) % static_cast<uint64_t>(n_local);
+    return __ldg(std_local + u * n_local + at);
+}
+
 // also: the two ranks of the pooled sample (world * s_slot values per unit) whose elements become the bracket pivots
 // (0xffffffff: open end / no select needed)
 __global__ void __launch_bounds__(256) tile_sample_kernel(const float *std_local, int64_t n_local, int64_t units, int s_slot,
@@ -1496,11 +1504,7 @@ __global__ void __launch_bounds__(256) tile_sample_kernel(const float *std_local
         rank_in[2 * u + 1] = rh;
     }
     if (i >= s_slot) return;
-    // hashed stride over the band; a band shorter than the slot is sampled with repetition
-    const uint64_t stride = static_cast<uint64_t>(n_local) >= static_cast<uint64_t>(s_slot) ? static_cast<uint64_t>(n_local) / s_slot : 1u;
-    const uint32_t jit = static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(i) * 0x9E3779B1u) * stride) >> 32);
-    const uint64_t at = (static_cast<uint64_t>(i) * stride + jit) % static_cast<uint64_t>(n_local);
-    out[u * s_slot + i] = __ldg(std_local + u * n_local + at);
+    out[u * s_slot + i] = tile_sample_value(std_local, n_local, u, s_slot, i);
 }
 
 // K4: pivots -> GsUnit (sweep state); units that need no select are answered here
@@ -1622,6 +1626,46 @@ __device__ __forceinline__ uint64_t global_ns() {
     return t;
 }
 
+// Every CTA of an exchanging grid calls p2p_ticket after its stores (all threads); it returns true in the last CTA to
+// arrive, which then (after any last-minute stores of its own) calls p2p_signal_wait with all of its threads.
+__device__ __forceinline__ bool p2p_ticket(unsigned char *const *windows, int rank, int region, uint32_t total_ctas, uint32_t *sh_last) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // bar.sync ordered the CTA's stores before this thread; its system-scope fence is cumulative over them
+        __threadfence_system();
+        P2pLocal *loc = reinterpret_cast<P2pLocal *>(windows[rank] + kP2pLocalOff);
+        *sh_last = (atomicAdd(&loc->done[region], 1u) == total_ctas - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    return *sh_last != 0u;
+}
+__device__ __forceinline__ void p2p_signal_wait(unsigned char *const *windows, int rank, int world, int region, uint32_t *status) {
+    const int tid = threadIdx.x;
+    P2pLocal *loc = reinterpret_cast<P2pLocal *>(windows[rank] + kP2pLocalOff);
+    __syncthreads();
+    if (tid == 0) __threadfence_system();
+    __syncthreads();
+    const uint32_t e = loc->epoch[region] + 1u;
+    if (tid < world) {
+        st_release_sys(reinterpret_cast<uint32_t *>(windows[tid] + kP2pFlagsOff) + region * kP2pMaxWorld + rank, e);
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(windows[rank] + kP2pFlagsOff) + region * kP2pMaxWorld + tid;
+        const uint64_t t0 = global_ns();
+        while (static_cast<int32_t>(ld_acquire_sys(mine) - e) < 0) {
+            __nanosleep(100);
+            if (global_ns() - t0 > 4000000000ull) {    // a peer never arrived (4 s): report instead of hanging the GPU
+                atomicAdd(&loc->error, 1u);
+                if (status) atomicAdd(status, 0x10000u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        loc->done[region] = 0u;
+        loc->epoch[region] = e;
+    }
+}
+
 // rows: `units` rows of this rank; row u = src[u * src_stride ..], `fixed_words` words long, or (fixed_words < 0) a
 // 4-word header + src[u * src_stride + 1] payload words.  Lands at window[dst_off + (u * world + rank) * dst_stride].
 // grid (chunks, units); the last CTA to finish signals and waits.
@@ -1672,37 +1716,44 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(unsigned char *const 
         uint4 *d4 = reinterpret_cast<uint4 *>(windows[p] + dst_off) + ((u * world + rank) * dst_stride >> 2);
         for (int64_t i = v0 + tid; i < v1; i += 256) d4[i] = (pk.st && i == 0) ? sh_head : __ldg(s4 + i);
     }
-    __syncthreads();
-    P2pLocal *loc = reinterpret_cast<P2pLocal *>(windows[rank] + kP2pLocalOff);
-    if (tid == 0) {
-        // bar.sync ordered the CTA's stores before this thread; its system-scope fence is cumulative over them
-        __threadfence_system();
-        const uint32_t total = gridDim.x * gridDim.y;
-        sh_last = (atomicAdd(&loc->done[region], 1u) == total - 1u) ? 1u : 0u;
+    if (p2p_ticket(windows, rank, region, gridDim.x * gridDim.y, &sh_last)) p2p_signal_wait(windows, rank, world, region, status);
+}
+
+// ---- first exchange folded into the kernel that produces the data -------------------------------------------------------
+// Sample + exchange: every sampled element is stored straight into all windows (coalesced 128-byte rows per warp).
+// (The same fusion for the sweep + second exchange -- every tile CTA appending its bracket elements to all windows --
+// was built and measured SLOWER: 0.371 vs 0.315 ms per 2-GPU step.  Each of the thousands of tile CTAs then needs a
+// system-scope fence before its ticket and the candidates leave as ~64-byte fragments, whereas the dedicated exchange
+// kernel moves them as 512-byte rows from 80 CTAs.  So the sweep keeps writing a local slot.)
+__global__ void __launch_bounds__(256) tile_sample_exchange_kernel(const float *std_local, int64_t n_local, int64_t units, int s_slot,
+                                                                   uint32_t *rank_in, int64_t n_total, float q01,
+                                                                   const float *q01_per_unit, unsigned char *const *windows, int rank,
+                                                                   int world, size_t dst_off, uint32_t *status) {
+    __shared__ uint32_t sh_last;
+    const int64_t u = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) {
+        const float q = q01_per_unit ? q01_per_unit[u] : q01;
+        const int S = world * s_slot;
+        uint32_t rl = 0xffffffffu, rh = 0xffffffffu;
+        if (unit_mode(q) == kModeThreshold) {
+            const TilePivotRanks t = tile_pivot_ranks(q, n_total, S);
+            if (t.klo > 0) rl = static_cast<uint32_t>(t.klo);
+            if (t.khi < S - 1) rh = static_cast<uint32_t>(t.khi);
+        }
+        rank_in[2 * u] = rl;
+        rank_in[2 * u + 1] = rh;
     }
-    __syncthreads();
-    if (sh_last == 0u) return;
-    if (tid == 0) __threadfence_system();
-    __syncthreads();
-    const uint32_t e = loc->epoch[region] + 1u;
-    if (tid < world) {
-        st_release_sys(reinterpret_cast<uint32_t *>(windows[tid] + kP2pFlagsOff) + region * kP2pMaxWorld + rank, e);
-        const uint32_t *mine = reinterpret_cast<const uint32_t *>(windows[rank] + kP2pFlagsOff) + region * kP2pMaxWorld + tid;
-        const uint64_t t0 = global_ns();
-        while (static_cast<int32_t>(ld_acquire_sys(mine) - e) < 0) {
-            __nanosleep(100);
-            if (global_ns() - t0 > 4000000000ull) {    // a peer never arrived (4 s): report instead of hanging the GPU
-                atomicAdd(&loc->error, 1u);
-                if (status) atomicAdd(status, 0x10000u);
-                break;
-            }
+    if (i < s_slot) {
+        const float v = tile_sample_value(std_local, n_local, u, s_slot, i);
+        const int64_t at = (u * world + rank) * s_slot + i;
+        for (int k = 0; k < world; ++k) {
+            int p = rank + k;
+            if (p >= world) p -= world;
+            reinterpret_cast<float *>(windows[p] + dst_off)[at] = v;
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        loc->done[region] = 0u;
-        loc->epoch[region] = e;
-    }
+    if (p2p_ticket(windows, rank, 0, gridDim.x * gridDim.y, &sh_last)) p2p_signal_wait(windows, rank, world, 0, status);
 }
 
 static int check_common(int64_t n_per_unit, int64_t units) {
@@ -2124,16 +2175,17 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
         PIC_CUDA_CHECK(cudaMemsetAsync(invalid, 0, 4, stream));
     }
     // 1. sample the band (and derive the pivot ranks of the pooled sample), exchange: unit u's pooled sample is contiguous
-    tile_sample_kernel<<<dim3((t.s_slot + 255) / 256, static_cast<unsigned>(units)), 256, 0, stream>>>(
-        std_local, n_local, units, t.s_slot, send_samp, rank_in, world, n_total, q01, q01_per_unit);
-    rc = launch_status();
-    if (rc != PIC_OK) return rc;
     if (p2p) {
-        p2p_exchange_kernel<<<dim3(4, static_cast<unsigned>(units)), 256, 0, stream>>>(
-            p2p->windows_dev, p2p->rank, world, 0, reinterpret_cast<const uint32_t *>(send_samp), t.s_slot, t.s_slot, x1_off,
-            t.s_slot, status_dev, P2pPack{nullptr, nullptr, 0, 0u});
+        // one kernel: the samples are stored straight into every rank's window
+        tile_sample_exchange_kernel<<<dim3((t.s_slot + 255) / 256, static_cast<unsigned>(units)), 256, 0, stream>>>(
+            std_local, n_local, units, t.s_slot, rank_in, n_total, q01, q01_per_unit, p2p->windows_dev, p2p->rank, world, x1_off,
+            status_dev);
         rc = launch_status();
     } else {
+        tile_sample_kernel<<<dim3((t.s_slot + 255) / 256, static_cast<unsigned>(units)), 256, 0, stream>>>(
+            std_local, n_local, units, t.s_slot, send_samp, rank_in, world, n_total, q01, q01_per_unit);
+        rc = launch_status();
+        if (rc != PIC_OK) return rc;
         // one all-gather per unit inside a group (a single fused NCCL launch)
         rc = nccl_status(nc.group_start());
         for (int64_t u = 0; u < units && rc == PIC_OK; ++u)
@@ -2154,7 +2206,8 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
                                                                                       q01_per_unit, thr_out);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
-    // 3. one sweep of the band: per-tile counts below the bracket, bracket elements straight into the exchange slot
+    // 3. one sweep of the band: per-tile counts below the bracket, bracket elements straight into the exchange slot;
+    // 4. exchange counts + candidates
     GsParams g{};
     g.std = std_local; g.q01_per_unit = q01_per_unit; g.q01 = q01; g.n = n_local; g.units = units;
     g.st = st; g.cand = send_x + 4; g.cand_cap = t.stride; g.below_tile = below_tile;
@@ -2164,7 +2217,6 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
     else gs_sweep_kernel<false, true><<<static_cast<unsigned>(units * t.tiles), kGsThreads, 0, stream>>>(g, t.tiles);
     rc = launch_status();
     if (rc != PIC_OK) return rc;
-    // 4. exchange counts + candidates, merge, exact select among the pooled candidates
     if (p2p) {
         // only the header (computed inside the exchange kernel) and the candidates that exist cross the links (NCCL has
         // to move the whole fixed-size slot)
@@ -2185,6 +2237,7 @@ int tiled_sampled_impl(const float *std_local, int64_t n_local, int64_t n_total,
         if (rc == PIC_OK) rc = rc_end;
     }
     if (rc != PIC_OK) return rc;
+    // 5. merge, exact select among the pooled candidates
     const int split = world >= 32 ? 1 : 32 / world;
     tile_merge_kernel<<<dim3(static_cast<unsigned>(world * split), static_cast<unsigned>(units)), 256, 0, stream>>>(
         all_x, world, split, units, t.stride, st, cand_all, t.cap_all, static_cast<uint32_t>(t.cap_x), n_total, q01, q01_per_unit,
