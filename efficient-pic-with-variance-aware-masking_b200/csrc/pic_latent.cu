@@ -1609,6 +1609,7 @@ __global__ void __launch_bounds__(256) tile_merge_kernel(const uint32_t *all_x, 
 // peer raises those only after (in stream order) it finished reading region R of call k.
 constexpr int kP2pMaxWorld = 64;
 constexpr size_t kP2pFlagsOff = 0, kP2pLocalOff = 1024, kP2pDataOff = 4096;
+__device__ unsigned long long g_p2p_timeout_ns = 4000000000ull;   // bounded wait for the peers' flags (PIC_P2P_TIMEOUT_MS)
 struct P2pLocal {
     uint32_t done[2], epoch[2], error, pad[3];
 };
@@ -1652,7 +1653,7 @@ __device__ __forceinline__ void p2p_signal_wait(unsigned char *const *windows, i
         const uint64_t t0 = global_ns();
         while (static_cast<int32_t>(ld_acquire_sys(mine) - e) < 0) {
             __nanosleep(100);
-            if (global_ns() - t0 > 4000000000ull) {    // a peer never arrived (4 s): report instead of hanging the GPU
+            if (global_ns() - t0 > g_p2p_timeout_ns) {    // a peer never arrived (default 4 s): report instead of hanging the GPU
                 atomicAdd(&loc->error, 1u);
                 if (status) atomicAdd(status, 0x10000u);
                 break;
@@ -2371,6 +2372,12 @@ int pic_dist_p2p_init(void *comm_, int rank, size_t sample_bytes, size_t cand_by
     uint32_t bad_total = 0;
     PIC_P2P_TRY(cudaMemcpy(&bad_total, flag_dev, 4, cudaMemcpyDeviceToHost));
     if (bad_total != 0u) return fail(PIC_ERR_CUDA);
+    if (const char *e = getenv("PIC_P2P_TIMEOUT_MS")) {     // ranks that may skew by more than the default 4 s raise it
+        long long ms = atoll(e);
+        if (ms < 100) ms = 100;
+        const unsigned long long ns = static_cast<unsigned long long>(ms) * 1000000ull;
+        PIC_P2P_TRY(cudaMemcpyToSymbol(g_p2p_timeout_ns, &ns, sizeof(ns)));
+    }
     PIC_P2P_TRY(cudaMalloc(&c->windows_dev, sizeof(unsigned char *) * kP2pMaxWorld));
     PIC_P2P_TRY(cudaMemcpy(c->windows_dev, c->window, sizeof(unsigned char *) * kP2pMaxWorld, cudaMemcpyHostToDevice));
     cudaFree(handles_dev);

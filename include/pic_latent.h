@@ -182,7 +182,7 @@ int pic_tiled_select_threshold_sampled(const float *std_local, int64_t n_local, 
  * between the steps and nothing is read back, so the whole select (and the apply behind it) captures into one CUDA
  * graph.  The price is that the validity check moves to the caller: *status_dev (device word, the caller zeroes it) counts
  * the units whose bracket missed or whose slot overflowed in its low 16 bits and adds 0x10000 per exchange wait that
- * timed out (a peer that never arrived: 4 s); when it is non-zero after the caller's next synchronisation the
+ * timed out (a peer that never arrived: 4 s by default, PIC_P2P_TIMEOUT_MS in the environment of pic_dist_p2p_init); when it is non-zero after the caller's next synchronisation the
  * thresholds of that call are not valid and (1c) has to be run instead -- every rank sees the same low 16 bits.
  * pic_dist_p2p_init / _destroy are collective over `comm` (they exchange the IPC handles and meet through it); the
  * regions are sized by pic_dist_p2p_region_bytes for the LARGEST (n_total, units) the window will serve.  One select at

@@ -977,3 +977,40 @@ def test_rem_model_derived(pic, dev, q_name):
             assert np.array_equal(N(gc.build_indexes(sc)), G[f"pr2.5/gc{i}/idx"]), i
         for i in range(int(G["pr2.5/n_idx"])):
             assert np.array_equal(N(gc.build_indexes(T(G[f"pr2.5/idx{i}/scales"], dev))), G[f"pr2.5/idx{i}/idx"]), i
+
+
+@pytest.mark.parametrize("q_name", ["pr2.5", "pr7"])
+def test_codec_loops_of_the_reference_model(pic, dev, q_name):
+    """The reference model's own codec loops (models/pic.py:809-820 compress, 942-948 decompress; recorded by
+    oracle/gen_golden_model_codec.py from the random-init model driven by the oracle coder) replayed on the CUDA drop-ins:
+    per progressive slice the block mask, the index of scale * mask and the symbols of the encoder, then the decoder's
+    side -- same mask and index from the same scale, the streams of the package's own coder decoded back to the encoder's
+    symbols, and the dequantised slice."""
+    G = golden("model_codec.npz")
+    masking = pic.ChannelMask("point-based-std")
+    gc = pic.GaussianConditional(None)
+    gc.update_scale_table(pic.get_scale_table())
+    gc = gc.to(dev)
+    pr = float(G[f"{q_name}/pr"])
+    for k in range(10):
+        tag = f"{q_name}/slice{k}"
+        scale = T(G[f"{tag}/scale"], dev)
+        want_mask = unpack_mask(G[f"{tag}/mask"], scale.shape)
+        # encoder (pic.py:809-820)
+        block_mask = masking(scale, pr=pr, mask_pol="point-based-std")
+        block_mask = masking.apply_noise(block_mask, False)
+        assert np.array_equal(N(block_mask), want_mask), k
+        index = gc.build_indexes(scale * block_mask).int()
+        assert np.array_equal(N(index), G[f"{tag}/idx"].astype(np.int32)), k
+        quant_in = T(G[f"{tag}/quant_in"], dev)
+        symbols = gc.quantize(quant_in, "symbols")
+        assert symbols.dtype == torch.int32 and np.array_equal(N(symbols), G[f"{tag}/symbols"]), k
+        strings = gc.compress(quant_in, index)
+        # decoder (pic.py:942-948): mask and index recomputed from the same scale, symbols from the stream
+        block_mask_d = masking(scale, pr=pr, mask_pol="point-based-std")
+        index_d = gc.build_indexes(scale * block_mask_d)
+        assert torch.equal(index_d.int(), index)
+        rv = gc.decompress(strings, index_d).reshape(scale.shape)
+        assert np.array_equal(N(rv).astype(np.int32), G[f"{tag}/symbols"]), k
+        y_hat = gc.dequantize(rv, T(G[f"{tag}/mu"], dev))
+        assert np.array_equal(N(y_hat), G[f"{tag}/y_hat"]), k

@@ -198,3 +198,26 @@ def test_rem_model_entropy_calls():
     for i in range(int(G["pr2.5/n_idx"])):
         sc = G[f"pr2.5/idx{i}/scales"].reshape(1, -1)
         assert np.array_equal(po.build_indexes(sc, table), G[f"pr2.5/idx{i}/idx"].reshape(1, -1)), i
+
+
+@pytest.mark.parametrize("q_name", ["pr2.5", "pr7"])
+def test_codec_loops_of_the_reference_model(q_name):
+    """models/pic.py:809-820 (compress) and 942-948 (decompress) of the random-init reference model, run with the oracle
+    coder (oracle/gen_golden_model_codec.py; the generator asserted that encoder and decoder agree on scale, mask, index
+    and symbols): per progressive slice the oracle reproduces the block mask, the index of scale * mask, the symbols of
+    (y - mu) * mask and the decoder's dequantised slice."""
+    G = golden("model_codec.npz")
+    table = scale_table()
+    pr = float(G[f"{q_name}/pr"])
+    for k in range(10):
+        tag = f"{q_name}/slice{k}"
+        scale = G[f"{tag}/scale"]
+        flat = scale.reshape(1, -1)
+        mask, _ = po.channel_mask(flat, pr)
+        assert np.array_equal(mask, unpack_mask(G[f"{tag}/mask"], flat.shape)), k
+        assert abs(mask.mean() - pr / 10) < 2e-3
+        assert np.array_equal(po.build_indexes(flat * mask, table), G[f"{tag}/idx"].reshape(1, -1).astype(np.int32)), k
+        sym = po.quantize(G[f"{tag}/quant_in"].reshape(1, -1), "symbols")
+        assert np.array_equal(sym, G[f"{tag}/symbols"].reshape(1, -1)), k
+        y_hat = sym.astype(np.float32) + G[f"{tag}/mu"].reshape(1, -1)       # entropy_models.py:161-168: type_as(means) + means
+        assert np.array_equal(y_hat, G[f"{tag}/y_hat"].reshape(1, -1)), k
