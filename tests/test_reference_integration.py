@@ -1,6 +1,6 @@
 """INTEGRATION.md section 1 ("change the import lines") checked against the reference model itself.  Needs the reference
-tree (PIC_REFERENCE_ROOT, default /root/reference): it exists in the build container only, so this is a CPU test that
-skips elsewhere -- the GPU box never sees the reference."""
+tree (oracle/ref_shim.py knows where: PIC_REFERENCE_ROOT or its default): it exists in the build container only, so this
+is a CPU test that skips elsewhere -- the GPU box never sees the reference."""
 import os
 import subprocess
 import sys
@@ -8,7 +8,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.environ.get("PIC_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_shim  # noqa: E402  (test infrastructure: locates the reference tree, imports nothing from it)
+
+REF = ref_shim.REFERENCE_ROOT
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "src", "models", "pic.py")), reason="reference tree not present")
