@@ -121,7 +121,8 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        use = inside if inside else anytime
+        # a GPU whose line of the one sample inside a short timed region arrived late falls back to its other samples
+        use = {g: (inside.get(g) or anytime.get(g)) for g in set(inside) | set(anytime)}
         med = {g: statistics.median(v) for g, v in use.items() if v}
         out = {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(smax) if smax else None,
                "reasons": sorted(reasons), "samples_in_timed_region": min((len(v) for v in inside.values()), default=0)}
