@@ -2051,7 +2051,7 @@ namespace {
 struct TiledPlan {
     int world, s_slot, S, tiles;
     int64_t cap_x, stride, cap_all;
-    size_t off_send_samp, off_all_samp, off_pooled, off_rank, off_piv, off_st, off_below, off_send_x, off_all_x, off_cand_all,
+    size_t off_send_samp, off_pooled, off_rank, off_piv, off_st, off_below, off_send_x, off_all_x, off_cand_all,
         off_invalid, off_rounds, total;
 };
 size_t up256(size_t v) { return (v + 255) / 256 * 256; }
@@ -2082,7 +2082,6 @@ bool tiled_plan(int64_t n_local, int64_t n_total, int64_t units, int world, doub
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += up256(bytes); return at; };
     t.off_send_samp = take(static_cast<size_t>(units) * s_slot * 4);
-    t.off_all_samp = take(static_cast<size_t>(world) * units * s_slot * 4);
     t.off_pooled = take(static_cast<size_t>(units) * t.S * 4);
     t.off_rank = take(static_cast<size_t>(units) * 8);
     t.off_piv = take(static_cast<size_t>(units) * 8);

@@ -128,13 +128,15 @@ class NcclTileComm:
         nothing synchronises (graph-capturable) and the caller reads p2p_status() at its next synchronisation point."""
         import ctypes
 
+        if protocol not in ("rounds", "sampled", "p2p"):
+            raise ValueError(f"unknown tiled-select protocol {protocol!r}")
+        if protocol == "p2p" and self._p2p is None:
+            raise RuntimeError("NcclTileComm.enable_p2p(n_total_max, units_max) has to run (on every rank) first")
         std_local = ops._require(std_local, "std_local")
         n_local = std_local.numel() // units
         q, qt = ops._q_args(q01, units, std_local.device)
         thr = torch.empty(units, dtype=torch.float32, device=std_local.device)
         if protocol == "p2p":
-            if self._p2p is None:
-                raise RuntimeError("NcclTileComm.enable_p2p(n_total_max, units_max) has to run (on every rank) first")
             need = int(lib().pic_tiled_sampled_workspace_bytes(n_local, n_total, units, self.world))
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=std_local.device)

@@ -190,3 +190,17 @@ def test_entropy_model_pickles_and_invalidates_its_table_cache():
         sd = fresh.state_dict()
         gc.load_state_dict(sd)
         assert gc._tables() is not t1
+
+
+def test_tiled_comm_requires_enable_p2p_before_the_p2p_protocol():
+    """distributed.NcclTileComm.select_threshold(protocol="p2p") without enable_p2p() is a caller error that must be
+    reported before anything is launched (checked on an object built without a communicator: no GPU, no NCCL here)."""
+    from pic_b200 import distributed as pdist
+
+    comm = object.__new__(pdist.NcclTileComm)
+    comm._p2p, comm._ws, comm.world, comm.fallbacks = None, None, 2, 0
+    std = torch.zeros(8)
+    with pytest.raises(RuntimeError, match="enable_p2p"):
+        comm.select_threshold(std, 1, 16, 0.5, protocol="p2p")
+    with pytest.raises(ValueError, match="protocol"):
+        comm.select_threshold(std, 1, 16, 0.5, protocol="ring")
