@@ -745,6 +745,102 @@ __global__ void __launch_bounds__(256) slice_apply_kernel(const SliceParams p, i
 }
 
 // ------------------------------------------------------------------------------------------
+// multi-quality apply (pic_slice_forward_multi).  Every output of an element depends on the quality level only through
+// its mask bit m = (std >= thr_level): the slice arithmetic is evaluated ONCE per element for m = 1 ("kept") and once
+// for m = 0 ("masked": mean substitution, the bound scale, symbol 0) with the very same routine the per-level kernel
+// uses (apply_pair), and each level then only compares, selects and stores -- ~10 instead of 87 lane-instructions
+// per output element, which turns the sweep from instruction-bound into store-bound.  One CTA = a 1024-element chunk
+// of one input unit x a group of levels.  grid = (chunks_per_unit * groups, input units); eval mode, 128-bit path.
+// ------------------------------------------------------------------------------------------
+constexpr int kMultiChunk = 1024;
+__global__ void __launch_bounds__(256) slice_apply_multi_kernel(const SliceParams p, int levels, int groups) {
+    constexpr int THREADS = 256;
+    static_assert(kMultiChunk == 4 * THREADS, "one float4 per thread");
+    __shared__ __align__(16) float tbl[kIndexSmemFloats];
+    __shared__ double red[THREADS / 32];
+    const int tid = threadIdx.x;
+    const IndexCtx ic = index_ctx_setup(p, tbl);
+    const int64_t u_in = blockIdx.y;
+    const int chunk = blockIdx.x / groups, grp = blockIdx.x - chunk * groups;
+    const int l0 = static_cast<int>(static_cast<int64_t>(levels) * grp / groups);
+    const int l1 = static_cast<int>(static_cast<int64_t>(levels) * (grp + 1) / groups);
+    const int64_t begin = static_cast<int64_t>(chunk) * kMultiChunk;
+    const int nvec = static_cast<int>(min(static_cast<int64_t>(kMultiChunk), p.n - begin)) >> 2;
+    const bool live = tid < nvec;
+    const int outs = outs_of(p);
+    const bool has_base = outs & 1, want_mask = outs & 2, want_yhat = outs & 4;
+    const bool want_lik = outs & (8 | 64), store_lik = outs & 8;
+    const bool want_idx = outs & 16, want_sym = outs & 32, want_rate = outs & 64;
+    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    const int64_t vin = ((u_in * p.n + begin) >> 2) + tid;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the other level groups of this chunk read the same lines: keep them in L2
+    const float4 sv = live ? ld_hint(reinterpret_cast<const float4 *>(p.std) + vin, pol_last) : zero4;
+    const float4 ytv = live ? ld_hint(reinterpret_cast<const float4 *>(p.y_top) + vin, pol_last) : zero4;
+    const float4 muv = live ? ld_hint(reinterpret_cast<const float4 *>(p.mu) + vin, pol_last) : zero4;
+    const float4 ybv = (live && has_base) ? ld_hint(reinterpret_cast<const float4 *>(p.y_base) + vin, pol_last) : zero4;
+    const float s[4] = {sv.x, sv.y, sv.z, sv.w}, yt[4] = {ytv.x, ytv.y, ytv.z, ytv.w};
+    const float yb[4] = {ybv.x, ybv.y, ybv.z, ybv.w}, mu[4] = {muv.x, muv.y, muv.z, muv.w};
+    const float nz[2] = {0.0f, 0.0f};
+    PairOut kept[2], gone[2];
+    float lg_kept[4] = {0.f, 0.f, 0.f, 0.f}, lg_gone[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        apply_pair<false>(s + 2 * h, yt + 2 * h, yb + 2 * h, mu + 2 * h, nz, has_base, 0.0f, true, p.scale_bound, p.lik_bound,
+                          want_lik, want_idx, want_sym, ic, kept[h]);
+        apply_pair<false>(s + 2 * h, yt + 2 * h, yb + 2 * h, mu + 2 * h, nz, has_base, __int_as_float(0x7fc00000), false,
+                          p.scale_bound, p.lik_bound, want_lik, want_idx, want_sym, ic, gone[h]);
+        if (want_rate) {
+            lg_kept[2 * h] = logf(kept[h].lik[0]); lg_kept[2 * h + 1] = logf(kept[h].lik[1]);
+            lg_gone[2 * h] = logf(gone[h].lik[0]); lg_gone[2 * h + 1] = logf(gone[h].lik[1]);
+        }
+    }
+    for (int l = l0; l < l1; ++l) {
+        const int64_t u = u_in * levels + l;
+        const int mode = unit_mode(p.q01_per_unit[u]);
+        const bool force_one = mode == kModeOnes;
+        const float thr = (mode == kModeThreshold) ? p.thr_in[u] : __int_as_float(0x7fc00000);   // s >= NaN is false
+        bool m[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[e] = (s[e] >= thr) || force_one;
+        float rate_acc = 0.0f;
+        if (live) {
+            const int64_t vi = ((u * p.n + begin) >> 2) + tid;
+            auto pick_f = [&](const float (&a)[2], const float (&b)[2], int e) { return m[e] ? a[e & 1] : b[e & 1]; };
+            auto pick_i = [&](const int32_t (&a)[2], const int32_t (&b)[2], int e) { return m[e] ? a[e & 1] : b[e & 1]; };
+            if (want_mask)
+                st_hint(reinterpret_cast<float4 *>(p.mask) + vi,
+                        make_float4(m[0] ? 1.f : 0.f, m[1] ? 1.f : 0.f, m[2] ? 1.f : 0.f, m[3] ? 1.f : 0.f), pol_first);
+            if (want_yhat)
+                st_hint(reinterpret_cast<float4 *>(p.y_hat) + vi,
+                        make_float4(pick_f(kept[0].y_hat, gone[0].y_hat, 0), pick_f(kept[0].y_hat, gone[0].y_hat, 1),
+                                    pick_f(kept[1].y_hat, gone[1].y_hat, 2), pick_f(kept[1].y_hat, gone[1].y_hat, 3)), pol_first);
+            if (store_lik)
+                st_hint(reinterpret_cast<float4 *>(p.lik) + vi,
+                        make_float4(pick_f(kept[0].lik, gone[0].lik, 0), pick_f(kept[0].lik, gone[0].lik, 1),
+                                    pick_f(kept[1].lik, gone[1].lik, 2), pick_f(kept[1].lik, gone[1].lik, 3)), pol_first);
+            if (want_idx)
+                st_hint(reinterpret_cast<int4 *>(p.idx) + vi,
+                        make_int4(pick_i(kept[0].idx, gone[0].idx, 0), pick_i(kept[0].idx, gone[0].idx, 1),
+                                  pick_i(kept[1].idx, gone[1].idx, 2), pick_i(kept[1].idx, gone[1].idx, 3)), pol_first);
+            if (want_sym)
+                st_hint(reinterpret_cast<int4 *>(p.symbols) + vi,
+                        make_int4(pick_i(kept[0].sym, gone[0].sym, 0), pick_i(kept[0].sym, gone[0].sym, 1),
+                                  pick_i(kept[1].sym, gone[1].sym, 2), pick_i(kept[1].sym, gone[1].sym, 3)), pol_first);
+            if (want_rate) {
+                // same pairwise order as the per-level kernel: (e0 + e1) of each pair, pairs in order
+                rate_acc += (m[0] ? lg_kept[0] : lg_gone[0]) + (m[1] ? lg_kept[1] : lg_gone[1]);
+                rate_acc += (m[2] ? lg_kept[2] : lg_gone[2]) + (m[3] ? lg_kept[3] : lg_gone[3]);
+            }
+        }
+        if (want_rate) {
+            const double total = block_sum_f64<THREADS>(rate_acc, red);
+            if (tid == 0) atomicAdd(&p.rate[u], total);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward of the slice
 // ------------------------------------------------------------------------------------------
 struct BwdParams {
@@ -2565,6 +2661,21 @@ int pic_slice_forward_multi(const float *y_top, const float *y_base, const float
     p.n = n_per_unit; p.units = units * levels; p.repeat = levels;
     p.mask = mask; p.y_hat = y_hat; p.lik = lik; p.idx = idx; p.symbols = symbols; p.rate = rate;
     p.apply_kind = 2;
+    static const int shared_eval = [] { const char *e = getenv("PIC_MULTI_SHARED_EVAL"); return e ? atoi(e) : 1; }();
+    if (shared_eval && levels >= 4 && slice_vec_ok(p) && units <= 65535) {
+        // kept / masked evaluation shared by the levels of a group: enough groups to fill the GPU about twice over, but at
+        // least 8 levels per group (the two full evaluations per element are what the group amortises)
+        const int64_t chunks = (n_per_unit + kMultiChunk - 1) / kMultiChunk;
+        int64_t groups = (2LL * sm_count() * 4 + units * chunks - 1) / (units * chunks);
+        if (groups > levels / 8) groups = levels / 8;
+        if (groups < 1) groups = 1;
+        if (chunks * groups <= 0x7fffffffLL) {
+            if (rate) PIC_CUDA_CHECK(cudaMemsetAsync(rate, 0, sizeof(double) * p.units, stream));
+            slice_apply_multi_kernel<<<dim3(static_cast<unsigned>(chunks * groups), static_cast<unsigned>(units)), 256, 0, stream>>>(
+                p, levels, static_cast<int>(groups));
+            return launch_status();
+        }
+    }
     return launch_apply(p, stream);
 }
 

@@ -937,6 +937,27 @@ def test_slice_forward_multi_quality_sweep(pic, dev):
             assert torch.equal(multi[k][:, l], one[k]), (k, pr)
         assert torch.equal(multi["thr"][:, l], one["thr"]), pr
         np.testing.assert_allclose(N(multi["rate"][:, l]), N(one["rate"]), rtol=1e-6)   # f32 partial sums, other order
+    # the shared kept / masked evaluation on hostile elements (NaN / inf / signed zeros in every input), a ragged unit size
+    # (a partial last chunk), no y_base, an output subset, 101 levels
+    units, n = 2, 5 * 1024 + 36
+    y_top, y_base, mu, std = trained_like(rng, (units, n))
+    for a in (y_top, mu, std):
+        a[0, :8] = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-30, -1e-30, 3e38]
+        a[1, 100:104] = [np.nan, -0.0, 0.0, np.inf]
+    mu[0, 8:12] = [0.0, -0.0, 0.0, -0.0]
+    y_top[0, 8:12] = [0.2, 0.2, -0.2, -0.2]          # round(d) = +-0 added to mu = +-0: the sign of the masked y_hat
+    y_top, mu, std = (T(a, dev) for a in (y_top, mu, std))
+    prs = [10.0 * k / 100 for k in range(101)]
+    want = ("mask", "y_hat", "lik", "symbols")
+    multi = pic.ops.slice_forward_multi(y_top, None, mu, std, units, prs, table, want=want)
+    for l in (0, 1, 17, 50, 99, 100):
+        one = pic.ops.slice_forward(y_top, None, mu, std, units, pic.ops.pr_to_q01(prs[l]), table, want=want + ("thr",))
+        for k in want:
+            a, b = multi[k][:, l], one[k]
+            same = (a == b) | ((a != a) & (b != b)) if a.dtype.is_floating_point else (a == b)
+            assert bool(same.all()), (k, prs[l])
+            if a.dtype.is_floating_point:        # signed zeros too
+                assert torch.equal(torch.signbit(a), torch.signbit(b)), (k, prs[l])
 
 
 # ------------------------------------------------------------------------------------------ REM model (config[3])
